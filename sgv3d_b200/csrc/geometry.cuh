@@ -1,0 +1,153 @@
+// Per-point ray -> height-plane geometry and voxel-index quantisation, bit-exact with the
+// reference's torch evaluation.  Restates (in fp32, with every rounding pinned by intrinsics so
+// that nvcc can neither contract nor reassociate):
+//   LSSFPN.get_geometry        layers/backbones/lss_fpn.py:372-401
+//   LSSFPN.height2localtion    layers/backbones/lss_fpn.py:350-370
+//   quantisation               layers/backbones/lss_fpn.py:487-488   ((g - lower) / size).int()
+// (identical code in layers/backbones/bsm_lss_fpn.py:409-460,552-553).
+//
+// Work that is invariant along the height-bin axis is hoisted per pixel WITHOUT changing any
+// rounding: the first two terms of every row of ida^-1 @ (u, v, z_d, 1) do not depend on d, and
+// the virtual-camera ray  pv = Mv @ (10x, 10y, 10, w)  is re-used for consecutive bins whenever
+// its inputs are bitwise unchanged (always, for the reference's z-preserving IDA matrices).
+#pragma once
+
+#include "common.cuh"
+
+namespace sgv3d {
+namespace geom {
+
+// Per-camera operands, staged in shared memory by the kernels (52 floats + bda).
+struct Camera {
+  float A[16];   // ida_mat.inverse()                         lss_fpn.py:392
+  float Mv[16];  // sensor2virtual @ inverse(intrin)          lss_fpn.py:361
+  float Me[16];  // sensor2ego @ inverse(sensor2virtual)      lss_fpn.py:367
+  float Bd[16];  // bda_mat (only read when has_bda)          lss_fpn.py:394-398
+  float ref_h;   // reference_heights[b, n]                   lss_fpn.py:352-354
+  int has_bda;
+};
+
+struct Grid {
+  float lower[3];  // fp32(voxel_coord - voxel_size / 2.0)
+  float size[3];   // voxel_size
+  int X, Y, Z;
+};
+
+template <int ARITH>
+__device__ __forceinline__ float dot4(const float *m, float b0, float b1, float b2, float b3) {
+  float acc = __fmul_rn(m[0], b0);
+  if (ARITH == SGV3D_ARITH_FMA) {
+    acc = __fmaf_rn(m[1], b1, acc);
+    acc = __fmaf_rn(m[2], b2, acc);
+    acc = __fmaf_rn(m[3], b3, acc);
+  } else {
+    acc = __fadd_rn(acc, __fmul_rn(m[1], b1));
+    acc = __fadd_rn(acc, __fmul_rn(m[2], b2));
+    acc = __fadd_rn(acc, __fmul_rn(m[3], b3));
+  }
+  return acc;
+}
+
+// first two terms of a row: m0*b0 (+) m1*b1
+template <int ARITH>
+__device__ __forceinline__ float dot2_head(const float *m, float b0, float b1) {
+  float acc = __fmul_rn(m[0], b0);
+  if (ARITH == SGV3D_ARITH_FMA) return __fmaf_rn(m[1], b1, acc);
+  return __fadd_rn(acc, __fmul_rn(m[1], b1));
+}
+// remaining two terms: (+) m2*b2 (+) m3*b3
+template <int ARITH>
+__device__ __forceinline__ float dot2_tail(float acc, const float *m, float b2, float b3) {
+  if (ARITH == SGV3D_ARITH_FMA) {
+    acc = __fmaf_rn(m[2], b2, acc);
+    return __fmaf_rn(m[3], b3, acc);
+  }
+  acc = __fadd_rn(acc, __fmul_rn(m[2], b2));
+  return __fadd_rn(acc, __fmul_rn(m[3], b3));
+}
+
+// State carried by one thread while it walks the height bins of one pixel.
+template <int ARITH>
+struct PixelRay {
+  float head[4];        // d-invariant partial sums of the four rows of  A @ (u, v, z, 1)
+  float q0, q1, q3;     // inputs of the cached virtual-camera ray
+  float pv0, pv1, pv2;  // cached  Mv @ (q0, q1, 10, q3)  (row 3 is overwritten with 1 downstream)
+  bool have_pv;
+
+  __device__ __forceinline__ void init(const Camera &cam, float u, float v) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) head[r] = dot2_head<ARITH>(cam.A + 4 * r, u, v);
+    have_pv = false;
+  }
+
+  // ego-frame point for height bin value z (lss_fpn.py:392 -> :398)
+  __device__ __forceinline__ void point(const Camera &cam, float z, float &gx, float &gy,
+                                        float &gz) {
+    // :392  p0 = ida^-1 @ (u, v, z, 1)
+    const float p0x = dot2_tail<ARITH>(head[0], cam.A + 0, z, 1.0f);
+    const float p0y = dot2_tail<ARITH>(head[1], cam.A + 4, z, 1.0f);
+    const float p0z = dot2_tail<ARITH>(head[2], cam.A + 8, z, 1.0f);
+    const float p0w = dot2_tail<ARITH>(head[3], cam.A + 12, z, 1.0f);
+    // :354  height = -1 * p0.z + reference_height
+    const float hgt = __fadd_rn(__fmul_rn(-1.0f, p0z), cam.ref_h);
+    // :356-360  ray through the pixel at virtual depth 10
+    const float n0 = __fmul_rn(p0x, 10.0f), n1 = __fmul_rn(p0y, 10.0f), n3 = p0w;
+    // :361-362  pv = (sensor2virtual @ K^-1) @ ray ; same bits in => same bits out, so re-use
+    if (!have_pv || __float_as_uint(n0) != __float_as_uint(q0) ||
+        __float_as_uint(n1) != __float_as_uint(q1) || __float_as_uint(n3) != __float_as_uint(q3)) {
+      q0 = n0; q1 = n1; q3 = n3;
+      pv0 = dot4<ARITH>(cam.Mv + 0, n0, n1, 10.0f, n3);
+      pv1 = dot4<ARITH>(cam.Mv + 4, n0, n1, 10.0f, n3);
+      pv2 = dot4<ARITH>(cam.Mv + 8, n0, n1, 10.0f, n3);
+      have_pv = true;
+    }
+    // :363-366  ratio = height / pv.y ; pe = pv * ratio ; pe.w = 1
+    const float ratio = __fdiv_rn(hgt, pv1);
+    const float e0 = __fmul_rn(pv0, ratio), e1 = __fmul_rn(pv1, ratio), e2 = __fmul_rn(pv2, ratio);
+    // :367-369  pg = (sensor2ego @ sensor2virtual^-1) @ pe
+    gx = dot4<ARITH>(cam.Me + 0, e0, e1, e2, 1.0f);
+    gy = dot4<ARITH>(cam.Me + 4, e0, e1, e2, 1.0f);
+    gz = dot4<ARITH>(cam.Me + 8, e0, e1, e2, 1.0f);
+    // :394-398  pg = bda @ pg
+    if (cam.has_bda) {
+      const float gw = dot4<ARITH>(cam.Me + 12, e0, e1, e2, 1.0f);
+      const float bx = dot4<ARITH>(cam.Bd + 0, gx, gy, gz, gw);
+      const float by = dot4<ARITH>(cam.Bd + 4, gx, gy, gz, gw);
+      const float bz = dot4<ARITH>(cam.Bd + 8, gx, gy, gz, gw);
+      gx = bx; gy = by; gz = bz;
+    }
+  }
+};
+
+// :487-488  ((g - lower) / size).int() -- fp32 subtract, IEEE divide, cvt.rzi.s32.f32
+// (truncation toward zero, saturating, NaN -> 0: what `.int()` does on a CUDA tensor).
+__device__ __forceinline__ int quantize1(float g, float lower, float size) {
+  return __float2int_rz(__fdiv_rn(__fsub_rn(g, lower), size));
+}
+
+// voxel id y*X + x of a kept point, -1 for a dropped one (voxel_pooling_forward_cuda.cu:24)
+__device__ __forceinline__ int voxel_of(const Grid &g, int ix, int iy, int iz) {
+  const bool kept = (unsigned)ix < (unsigned)g.X && (unsigned)iy < (unsigned)g.Y &&
+                    (unsigned)iz < (unsigned)g.Z;
+  return kept ? iy * g.X + ix : -1;
+}
+
+// cooperative load of one camera's operands into shared memory
+__device__ __forceinline__ void load_camera(Camera *s, const float *ida_inv, const float *mv,
+                                            const float *me, const float *bda, const float *ref_h,
+                                            int bn, int b) {
+  const int t = threadIdx.x;
+  if (t < 16) {
+    s->A[t] = ida_inv[16 * (size_t)bn + t];
+    s->Mv[t] = mv[16 * (size_t)bn + t];
+    s->Me[t] = me[16 * (size_t)bn + t];
+    s->Bd[t] = bda ? bda[16 * (size_t)b + t] : 0.0f;
+  }
+  if (t == 0) {
+    s->ref_h = ref_h[bn];
+    s->has_bda = bda != nullptr;
+  }
+}
+
+}  // namespace geom
+}  // namespace sgv3d

@@ -1,0 +1,686 @@
+// Fused lift-splat for B200 (sm_100a): the B x Nc x D x fH x fW x C frustum tensor of the reference
+// (layers/backbones/lss_fpn.py:464-466,486,490) is never materialised.
+//
+// Key identity: along the height-bin axis D consecutive bins of one pixel fall into the same
+// voxel in runs, and  sum_{d in run} p_d * ctx_c = (sum_{d in run} p_d) * ctx_c.  So the scatter
+//   BEV[b,c,voxel] += height[d,pixel] * ctx[c,pixel]          (N*C multiply-adds per frame)
+// becomes a sparse (voxel x pixel) weighted gather of whole context rows with
+// nnz = #runs (3-7x fewer than points; SURVEY.md §7 hard part 3).
+//
+//   PLAN   (index; depends on calibration + grid only)
+//     ls_plan_runs_kernel     thread/pixel walks D: bit-exact geometry -> voxel id -> run-length
+//                             encoding, emitted pixel-major in an ELL layout; digit histogram
+//     scan / scatter / hist / scan / scatter   stable 2-pass radix sort of the runs by voxel
+//     row_ptr_kernel          CSR offsets per voxel + inverse permutation (run -> sorted slot)
+//   FORWARD (values)
+//     transpose_pad_kernel    context NCHW -> one 16B-aligned row per pixel
+//     ls_weights_kernel       w[run] = sum_{d in run} height[d,pixel]   (coalesced, lockstep in d)
+//     ls_reduce_kernel        per voxel: sum_j w[j] * ctx_row[pixel_j] in sorted (deterministic)
+//                             order, staged through smem, written NCHW-coalesced incl. zero rows
+//   BACKWARD (values; pixel-major, no sort needed)
+//     transpose_pad_kernel    grad_bev NCHW -> one row per voxel
+//     ls_weights_kernel       w per run (pixel-major destination)
+//     ls_backward_gather_kernel  warp/pixel: g_ctx_row = sum_r w_r*G[voxel_r]; gw_r = <ctx_row, G[voxel_r]>
+//     ls_expand_gheight_kernel   g_height[d,pixel] = gw[run(d)] (0 for dropped bins), coalesced
+//     transpose_pad_kernel    g_ctx rows -> NCHW
+//
+// No floating-point atomics anywhere; every sum has a fixed order => bitwise reproducible.
+#include <cuda_bf16.h>
+
+#include "geometry.cuh"
+#include "sort.cuh"
+#include "transpose.cuh"
+
+namespace sgv3d {
+namespace {
+
+constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
+
+struct Dims {
+  int B, Nc, D, fH, fW, C, X, Y, Z;
+  int P;        // fH*fW pixels per camera
+  int cpc;      // chunks per camera
+  int nchunks;  // chunks per frame = Nc*cpc
+  int V;        // X*Y voxels per frame
+  int Cpad;     // padded row length of the channels-last copies (elements)
+  int cap;      // max runs per frame (= ELL slots per frame)
+  int bins2, nblk2;
+};
+
+struct Workspace {
+  int *count, *run_cnt, *run_vox, *run_d, *run_dst, *hist1, *keys1, *pay1, *hist2, *keys2,
+      *vm_pix, *row_ptr;
+  float *w_vm, *w_pm, *gw_pm, *gT, *gctxT;
+  void *ctxT;
+  size_t bytes;
+};
+
+Dims make_dims(const sgv3d_lift_splat_desc *d) {
+  Dims m;
+  m.B = d->B; m.Nc = d->Nc; m.D = d->D; m.fH = d->fH; m.fW = d->fW; m.C = d->C;
+  m.X = d->X; m.Y = d->Y; m.Z = d->Z;
+  m.P = m.fH * m.fW;
+  m.cpc = ceil_div(m.P, kChunk);
+  m.nchunks = m.Nc * m.cpc;
+  m.V = m.X * m.Y;
+  const int q = d->ctx_dtype == SGV3D_DTYPE_BF16 ? 8 : 4;
+  m.Cpad = ceil_div(m.C, q) * q;
+  m.cap = m.nchunks * kChunk * m.D;
+  m.bins2 = (m.V >> sort::kLowBits) + 1;
+  m.nblk2 = ceil_div(m.cap, sort::kItemsPerBlock);
+  return m;
+}
+
+Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
+  Workspace w;
+  Carver c(ws);
+  const size_t B = m.B, slots = (size_t)m.B * m.cap;
+  w.count = c.take<int>(B);
+  w.run_cnt = c.take<int>(B * m.nchunks * kChunk);
+  w.run_vox = c.take<int>(slots);
+  w.run_d = c.take<int>(slots);
+  w.run_dst = c.take<int>(slots);
+  w.hist1 = c.take<int>(B * sort::kLowBins * m.nchunks);
+  w.keys1 = c.take<int>(slots);
+  w.pay1 = c.take<int>(slots);
+  w.hist2 = c.take<int>(B * m.bins2 * m.nblk2);
+  w.keys2 = c.take<int>(slots);
+  w.vm_pix = c.take<int>(slots);
+  w.row_ptr = c.take<int>(B * (m.V + 1));
+  w.w_vm = c.take<float>(slots);
+  w.w_pm = c.take<float>(slots);
+  w.gw_pm = c.take<float>(slots);
+  const size_t rows = B * m.Nc * m.P;
+  if (ctx_dtype == SGV3D_DTYPE_BF16) w.ctxT = c.take<__nv_bfloat16>(rows * m.Cpad);
+  else w.ctxT = c.take<float>(rows * m.Cpad);
+  const int gpad = ceil_div(m.C, 4) * 4;
+  w.gT = c.take<float>(B * m.V * gpad);
+  w.gctxT = c.take<float>(rows * gpad);
+  w.bytes = c.used();
+  return w;
+}
+
+__device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t) {
+  return ((size_t)frame_chunk * D + r) * kChunk + t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLAN 1/3: geometry -> voxel id per height bin -> runs.  grid (nchunks, B), 128 threads.
+// ---------------------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void __launch_bounds__(kChunk)
+ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__restrict__ v_tab,
+                    const float *__restrict__ z_tab, const float *__restrict__ ida_inv,
+                    const float *__restrict__ mv, const float *__restrict__ me,
+                    const float *__restrict__ bda, const float *__restrict__ ref_h, geom::Grid grid,
+                    int *__restrict__ run_cnt, int *__restrict__ run_vox, int *__restrict__ run_d,
+                    int *__restrict__ hist1) {
+  __shared__ geom::Camera cam;
+  __shared__ int s_hist[sort::kLowBins];
+  extern __shared__ float z_s[];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int bn = b * m.Nc + n;
+  const int t = threadIdx.x;
+  geom::load_camera(&cam, ida_inv, mv, me, bda, ref_h, bn, b);
+  for (int d = t; d < m.D; d += kChunk) z_s[d] = z_tab[d];
+  for (int i = t; i < sort::kLowBins; i += kChunk) s_hist[i] = 0;
+  __syncthreads();
+  const int frame_chunk = b * m.nchunks + chunk;
+  const int p = ci * kChunk + t;
+  int r = 0;
+  if (p < m.P) {
+    const int h = p / m.fW, w = p - h * m.fW;
+    geom::PixelRay<ARITH> ray;
+    ray.init(cam, u_tab[w], v_tab[h]);
+    int cur = -1, d0 = 0;
+    for (int d = 0; d <= m.D; ++d) {
+      int vox = -2;  // sentinel closing the last run
+      if (d < m.D) {
+        float gx, gy, gz;
+        ray.point(cam, z_s[d], gx, gy, gz);
+        vox = geom::voxel_of(grid, geom::quantize1(gx, grid.lower[0], grid.size[0]),
+                             geom::quantize1(gy, grid.lower[1], grid.size[1]),
+                             geom::quantize1(gz, grid.lower[2], grid.size[2]));
+      }
+      if (vox != cur) {
+        if (cur >= 0) {
+          const size_t s = ell_slot(frame_chunk, m.D, r, t);
+          run_vox[s] = cur;
+          run_d[s] = d0 | (d << 16);
+          atomicAdd(&s_hist[cur & (sort::kLowBins - 1)], 1);
+          ++r;
+        }
+        cur = vox;
+        d0 = d;
+      }
+    }
+  }
+  run_cnt[(size_t)frame_chunk * kChunk + t] = r;
+  __syncthreads();
+  int *hh = hist1 + (size_t)b * sort::kLowBins * m.nchunks;
+  for (int i = t; i < sort::kLowBins; i += kChunk) hh[(size_t)i * m.nchunks + chunk] = s_hist[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLAN 2/3: first radix pass straight out of the ELL layout.  Block = chunk, warp w owns the
+// pixels t = 32w + lane, iteration = run index r.  Payload = frame-local ELL slot.
+// ---------------------------------------------------------------------------------------------
+struct EllInput {
+  const int *run_vox;
+  int frame_chunk, chunk, D;
+  int cnt;     // runs of this thread's pixel
+  int warp_max;
+  __device__ __forceinline__ int iters(int) const { return warp_max; }
+  __device__ __forceinline__ bool load(int w, int it, int lane, int &key, int &pay) const {
+    if (it >= cnt) return false;
+    const int t = w * 32 + lane;
+    key = run_vox[ell_slot(frame_chunk, D, it, t)];
+    pay = (chunk * D + it) * kChunk + t;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(kChunk)
+ls_scatter_ell_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_vox,
+                      const int *__restrict__ gbase1, int *__restrict__ keys1,
+                      int *__restrict__ pay1) {
+  __shared__ int s_cnt[(kChunk / 32) * sort::kLowBins];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int frame_chunk = b * m.nchunks + chunk;
+  EllInput in;
+  in.run_vox = run_vox;
+  in.frame_chunk = frame_chunk;
+  in.chunk = chunk;
+  in.D = m.D;
+  in.cnt = run_cnt[(size_t)frame_chunk * kChunk + threadIdx.x];
+  in.warp_max = __reduce_max_sync(0xffffffffu, in.cnt);
+  sort::stable_scatter_block<kChunk / 32>(in, sort::DigitOf<0, sort::kLowBins - 1>(), sort::kLowBins,
+                                          gbase1 + (size_t)b * sort::kLowBins * m.nchunks, m.nchunks,
+                                          chunk, s_cnt, keys1 + (size_t)b * m.cap,
+                                          pay1 + (size_t)b * m.cap);
+}
+
+// PLAN 3/3 epilogue functor: inverse permutation + frame-local pixel id per sorted run.
+struct PlanFinalize {
+  Dims m;
+  int *pay2_to_pix;  // in: ELL slot, out: frame-local pixel (n*P + p)
+  int *run_dst;
+  __device__ __forceinline__ void operator()(int frame, int j) const {
+    int *pp = pay2_to_pix + (size_t)frame * m.cap;
+    const int slot = pp[j];
+    run_dst[(size_t)frame * m.cap + slot] = j;
+    const int t = slot & (kChunk - 1);
+    const int chunk = (slot / kChunk) / m.D;
+    const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+    pp[j] = n * m.P + ci * kChunk + t;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FORWARD / BACKWARD: run weights  w = sum_{d in run} height[d, pixel].
+// Thread per pixel, all lanes walk d in lockstep so every height row is read fully coalesced,
+// exactly once.  DST_SORTED: write to the run's voxel-major slot (forward) else pixel-major ELL.
+// ---------------------------------------------------------------------------------------------
+template <bool DST_SORTED>
+__global__ void __launch_bounds__(kChunk)
+ls_weights_kernel(Dims m, const float *__restrict__ height, const int *__restrict__ run_cnt,
+                  const int *__restrict__ run_d, const int *__restrict__ run_dst,
+                  float *__restrict__ w_out) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int frame_chunk = b * m.nchunks + chunk;
+  const int t = threadIdx.x;
+  const int p = ci * kChunk + t;
+  if (p >= m.P) return;
+  const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
+  if (cnt == 0) return;
+  const float *hp = height + (size_t)(b * m.Nc + n) * m.D * m.P + p;
+  int r = 0;
+  size_t s = ell_slot(frame_chunk, m.D, 0, t);
+  int packed = run_d[s];
+  int d0 = packed & 0xffff, d1 = packed >> 16;
+  float acc = 0.0f;
+  // every lane starts at d = 0 so that the warp reads each height row as one coalesced request
+  for (int d = 0; d < m.D; ++d) {
+    const float hv = ldg_stream_f1(hp + (size_t)d * m.P);
+    if (d >= d0) acc = __fadd_rn(acc, hv);
+    if (d + 1 == d1) {
+      const size_t o = DST_SORTED ? (size_t)b * m.cap + run_dst[s] : s;
+      w_out[o] = acc;
+      acc = 0.0f;
+      if (++r == cnt) break;
+      s = ell_slot(frame_chunk, m.D, r, t);
+      packed = run_d[s];
+      d0 = packed & 0xffff;
+      d1 = packed >> 16;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FORWARD: per-voxel weighted gather of context rows.
+// grid (ceil(V/32), B), 256 threads.  CTA = 32 consecutive voxels (one 128-byte strip of every
+// output channel plane); warp w owns voxels 4w..4w+3; lanes own 4-channel slices of a row.
+// ---------------------------------------------------------------------------------------------
+template <typename CT>
+struct RowLoad;
+template <>
+struct RowLoad<float> {
+  static __device__ __forceinline__ void load(const float *row, int slice, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(row) + slice);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <>
+struct RowLoad<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16 *row, int slice, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(row) + slice);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+};
+
+constexpr int kTileV = 32;
+
+template <typename CT, int NCH>
+__global__ void __launch_bounds__(256)
+ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
+                 const int *__restrict__ vm_pix, const float *__restrict__ w_vm,
+                 float *__restrict__ bev) {
+  extern __shared__ float tile[];  // [C][kTileV + 1]
+  const int b = blockIdx.y;
+  const int v0 = blockIdx.x * kTileV;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int *rp = row_ptr + (size_t)b * (m.V + 1);
+  const int vend = min(v0 + kTileV, m.V);
+  float *out = bev + (size_t)b * m.C * m.V;
+  const int tile_lo = rp[v0], tile_hi = rp[vend];
+  if (tile_lo == tile_hi) {  // empty strip: zero rows only
+    for (int c = wid; c < m.C; c += 8)
+      if (v0 + lane < vend) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, 0.0f);
+    return;
+  }
+  const int nslices = m.Cpad / 4;
+  const CT *rows = ctxT + (size_t)b * m.Nc * m.P * m.Cpad;
+  const int *pix = vm_pix + (size_t)b * m.cap;
+  const float *wv = w_vm + (size_t)b * m.cap;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const int vl = wid * 4 + i;
+    const int v = v0 + vl;
+    float acc[NCH][4];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
+    if (v < vend) {
+      const int lo = rp[v], hi = rp[v + 1];
+      for (int j0 = lo; j0 < hi; j0 += 32) {
+        const int cnt = min(32, hi - j0);
+        int my_pix = 0;
+        float my_w = 0.0f;
+        if (lane < cnt) {
+          my_pix = pix[j0 + lane];
+          my_w = wv[j0 + lane];
+        }
+        int q = 0;
+        for (; q + 4 <= cnt; q += 4) {  // 4 independent row loads in flight
+          float r[4][NCH][4];
+          float ww[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const CT *row = rows + (size_t)__shfl_sync(0xffffffffu, my_pix, q + u) * m.Cpad;
+            ww[u] = __shfl_sync(0xffffffffu, my_w, q + u);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const int sl = k * 32 + lane;
+              if (sl < nslices) RowLoad<CT>::load(row, sl, r[u][k]);
+              else { r[u][k][0] = r[u][k][1] = r[u][k][2] = r[u][k][3] = 0.0f; }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(ww[u], r[u][k][e], acc[k][e]);
+        }
+        for (; q < cnt; ++q) {
+          const CT *row = rows + (size_t)__shfl_sync(0xffffffffu, my_pix, q) * m.Cpad;
+          const float w1 = __shfl_sync(0xffffffffu, my_w, q);
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const int sl = k * 32 + lane;
+            if (sl < nslices) {
+              float r1[4];
+              RowLoad<CT>::load(row, sl, r1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(w1, r1[e], acc[k][e]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = (k * 32 + lane) * 4 + e;
+        if (c < m.C) tile[c * (kTileV + 1) + vl] = acc[k][e];
+      }
+  }
+  __syncthreads();
+  for (int c = wid; c < m.C; c += 8)
+    if (v0 + lane < vend) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, tile[c * (kTileV + 1) + lane]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BACKWARD: one warp per pixel.  Lanes hold 4-channel slices of the pixel's context row;
+// for every run: G row gather (128-bit), g_ctx += w*G, gw = <ctx, G> (fixed butterfly order).
+// ---------------------------------------------------------------------------------------------
+template <typename CT, int NCH>
+__global__ void __launch_bounds__(256)
+ls_backward_gather_kernel(Dims m, int gpad, const CT *__restrict__ ctxT, const float *__restrict__ gT,
+                          const int *__restrict__ run_cnt, const int *__restrict__ run_vox,
+                          const float *__restrict__ w_pm, float *__restrict__ gw_pm,
+                          float *__restrict__ gctxT) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int fp = blockIdx.x * 8 + (threadIdx.x >> 5);  // frame-local pixel n*P + p
+  if (fp >= m.Nc * m.P) return;
+  const int n = fp / m.P, p = fp - n * m.P;
+  const int ci = p / kChunk, t = p - ci * kChunk;
+  const int frame_chunk = b * m.nchunks + n * m.cpc + ci;
+  const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
+  const size_t row_id = (size_t)b * m.Nc * m.P + fp;
+  const int nslices_c = m.Cpad / 4, nslices_g = gpad / 4;
+  float cx[NCH][4], acc[NCH][4];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int sl = k * 32 + lane;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { cx[k][e] = 0.0f; acc[k][e] = 0.0f; }
+    if (sl < nslices_c && cnt > 0) RowLoad<CT>::load(ctxT + row_id * m.Cpad, sl, cx[k]);
+  }
+  const float *gb = gT + (size_t)b * m.V * gpad;
+  for (int r0 = 0; r0 < cnt; r0 += 32) {
+    const int nr = min(32, cnt - r0);
+    int my_vox = 0;
+    float my_w = 0.0f;
+    if (lane < nr) {
+      const size_t s = ell_slot(frame_chunk, m.D, r0 + lane, t);
+      my_vox = run_vox[s];
+      my_w = w_pm[s];
+    }
+    float my_gw = 0.0f;
+    for (int q = 0; q < nr; ++q) {
+      const float *grow = gb + (size_t)__shfl_sync(0xffffffffu, my_vox, q) * gpad;
+      const float w1 = __shfl_sync(0xffffffffu, my_w, q);
+      float dot = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int sl = k * 32 + lane;
+        if (sl < nslices_g) {
+          const float4 g = __ldg(reinterpret_cast<const float4 *>(grow) + sl);
+          acc[k][0] = __fmaf_rn(w1, g.x, acc[k][0]);
+          acc[k][1] = __fmaf_rn(w1, g.y, acc[k][1]);
+          acc[k][2] = __fmaf_rn(w1, g.z, acc[k][2]);
+          acc[k][3] = __fmaf_rn(w1, g.w, acc[k][3]);
+          dot = __fmaf_rn(cx[k][0], g.x, dot);
+          dot = __fmaf_rn(cx[k][1], g.y, dot);
+          dot = __fmaf_rn(cx[k][2], g.z, dot);
+          dot = __fmaf_rn(cx[k][3], g.w, dot);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, o));
+      if (lane == q) my_gw = dot;
+    }
+    if (lane < nr) gw_pm[ell_slot(frame_chunk, m.D, r0 + lane, t)] = my_gw;
+  }
+  float *dst = gctxT + row_id * gpad;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int sl = k * 32 + lane;
+    if (sl < nslices_g)
+      *(reinterpret_cast<float4 *>(dst) + sl) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+  }
+}
+
+// g_height[d, pixel] = gw[run containing d], 0 for dropped bins.  Thread per pixel, lockstep in d.
+// EXPAND_VOX: write the voxel id instead (plan_expand debug entry point).
+template <bool EXPAND_VOX>
+__global__ void __launch_bounds__(kChunk)
+ls_expand_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_d,
+                 const int *__restrict__ run_vox, const float *__restrict__ gw_pm,
+                 float *__restrict__ g_height, int *__restrict__ vox_out) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int frame_chunk = b * m.nchunks + chunk;
+  const int t = threadIdx.x;
+  const int p = ci * kChunk + t;
+  if (p >= m.P) return;
+  const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
+  const size_t base = (size_t)(b * m.Nc + n) * m.D * m.P + p;
+  int r = 0, d0 = m.D, d1 = m.D;
+  float gv = 0.0f;
+  int vv = -1;
+  if (cnt > 0) {
+    const size_t s = ell_slot(frame_chunk, m.D, 0, t);
+    const int packed = run_d[s];
+    d0 = packed & 0xffff; d1 = packed >> 16;
+    if (EXPAND_VOX) vv = run_vox[s]; else gv = gw_pm[s];
+  }
+  for (int d = 0; d < m.D; ++d) {
+    const bool in = d >= d0 && d < d1;
+    if (EXPAND_VOX) vox_out[base + (size_t)d * m.P] = in ? vv : -1;
+    else stg_stream_f1(g_height + base + (size_t)d * m.P, in ? gv : 0.0f);
+    if (d + 1 == d1) {
+      if (++r < cnt) {
+        const size_t s = ell_slot(frame_chunk, m.D, r, t);
+        const int packed = run_d[s];
+        d0 = packed & 0xffff; d1 = packed >> 16;
+        if (EXPAND_VOX) vv = run_vox[s]; else gv = gw_pm[s];
+      } else {
+        d0 = d1 = m.D + 1;
+      }
+    }
+  }
+}
+
+int validate(const sgv3d_lift_splat_desc *d, const char *who) {
+  SGV3D_REQUIRE(d != nullptr, "%s: desc is null", who);
+  SGV3D_REQUIRE(d->B >= 0 && d->Nc > 0 && d->D > 0 && d->fH > 0 && d->fW > 0 && d->C > 0 && d->X > 0 &&
+                    d->Y > 0 && d->Z > 0, "%s: bad sizes", who);
+  SGV3D_REQUIRE(d->B <= 65535, "%s: B > 65535", who);
+  SGV3D_REQUIRE(d->D < 32768, "%s: D=%d too large", who, d->D);
+  SGV3D_REQUIRE(d->C <= 256, "%s: C=%d > 256 unsupported by the fused path", who, d->C);
+  SGV3D_REQUIRE((long long)d->X * d->Y < (long long)sort::kMaxHighBins << sort::kLowBits,
+                "%s: X*Y exceeds %d voxels per frame", who, sort::kMaxHighBins << sort::kLowBits);
+  SGV3D_REQUIRE(d->arith == SGV3D_ARITH_SEQ || d->arith == SGV3D_ARITH_FMA, "%s: bad arith", who);
+  SGV3D_REQUIRE(d->ctx_dtype == SGV3D_DTYPE_F32 || d->ctx_dtype == SGV3D_DTYPE_BF16, "%s: bad ctx_dtype", who);
+  const long long slots = (long long)d->Nc * ceil_div(d->fH * d->fW, kChunk) * kChunk * d->D;
+  SGV3D_REQUIRE(slots < (1ll << 31), "%s: more than 2^31 height-bin slots per frame", who);
+  return SGV3D_OK;
+}
+
+int check_ws(const Workspace &w, void *ws, size_t bytes, const char *who) {
+  if (!ws || bytes < w.bytes) {
+    set_error("%s: workspace %zu < required %zu bytes", who, bytes, w.bytes);
+    return SGV3D_ERR_WORKSPACE_TOO_SMALL;
+  }
+  return SGV3D_OK;
+}
+
+template <typename CT>
+int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+  dim3 grid(ceil_div(m.V, kTileV), m.B);
+  const size_t smem = sizeof(float) * m.C * (kTileV + 1);
+  const CT *ctxT = static_cast<const CT *>(w.ctxT);
+  if (m.Cpad <= 128)
+    ls_reduce_kernel<CT, 1><<<grid, 256, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
+  else
+    ls_reduce_kernel<CT, 2><<<grid, 256, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
+  SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
+  return SGV3D_OK;
+}
+
+template <typename CT>
+int launch_backward_gather(const Dims &m, const Workspace &w, int gpad, cudaStream_t s) {
+  dim3 grid(ceil_div(m.Nc * m.P, 8), m.B);
+  const CT *ctxT = static_cast<const CT *>(w.ctxT);
+  if (m.Cpad <= 128)
+    ls_backward_gather_kernel<CT, 1><<<grid, 256, 0, s>>>(m, gpad, ctxT, w.gT, w.run_cnt, w.run_vox,
+                                                          w.w_pm, w.gw_pm, w.gctxT);
+  else
+    ls_backward_gather_kernel<CT, 2><<<grid, 256, 0, s>>>(m, gpad, ctxT, w.gT, w.run_cnt, w.run_vox,
+                                                          w.w_pm, w.gw_pm, w.gctxT);
+  SGV3D_CHECK_LAUNCH("ls_backward_gather_kernel");
+  return SGV3D_OK;
+}
+
+int transpose_context(const Dims &m, const Workspace &w, int ctx_dtype, const void *context,
+                      cudaStream_t s) {
+  const int batch = m.B * m.Nc;
+  if (ctx_dtype == SGV3D_DTYPE_BF16)
+    launch_transpose_pad<__nv_bfloat16, __nv_bfloat16>(
+        static_cast<const __nv_bfloat16 *>(context), static_cast<__nv_bfloat16 *>(w.ctxT), batch, m.C,
+        m.P, m.P, (size_t)m.C * m.P, m.Cpad, (size_t)m.P * m.Cpad, s);
+  else
+    launch_transpose_pad<float, float>(static_cast<const float *>(context), static_cast<float *>(w.ctxT),
+                                       batch, m.C, m.P, m.P, (size_t)m.C * m.P, m.Cpad,
+                                       (size_t)m.P * m.Cpad, s);
+  SGV3D_CHECK_LAUNCH("transpose_pad_kernel(context)");
+  return SGV3D_OK;
+}
+
+}  // namespace
+}  // namespace sgv3d
+
+using namespace sgv3d;
+
+extern "C" size_t sgv3d_lift_splat_workspace_bytes(const sgv3d_lift_splat_desc *desc) {
+  if (validate(desc, "lift_splat_workspace_bytes") != SGV3D_OK || desc->B == 0) return 0;
+  const Dims m = make_dims(desc);
+  return carve(nullptr, m, desc->ctx_dtype).bytes;
+}
+
+extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const float *u_tab,
+                                     const float *v_tab, const float *z_tab, const float *ida_inv,
+                                     const float *m_virtual, const float *m_ego, const float *bda,
+                                     const float *ref_heights, const float *lower3,
+                                     const float *size3, void *workspace, size_t workspace_bytes,
+                                     sgv3d_stream_t stream) {
+  if (int rc = validate(desc, "lift_splat_plan")) return rc;
+  if (desc->B == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(u_tab && v_tab && z_tab && ida_inv && m_virtual && m_ego && ref_heights && lower3 && size3,
+                "lift_splat_plan: null pointer");
+  const Dims m = make_dims(desc);
+  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  geom::Grid grid;
+  for (int k = 0; k < 3; ++k) { grid.lower[k] = lower3[k]; grid.size[k] = size3[k]; }
+  grid.X = m.X; grid.Y = m.Y; grid.Z = m.Z;
+
+  dim3 gc(m.nchunks, m.B);
+  const size_t zsm = sizeof(float) * m.D;
+  if (desc->arith == SGV3D_ARITH_FMA)
+    ls_plan_runs_kernel<SGV3D_ARITH_FMA><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
+                                                               m_ego, bda, ref_heights, grid, w.run_cnt,
+                                                               w.run_vox, w.run_d, w.hist1);
+  else
+    ls_plan_runs_kernel<SGV3D_ARITH_SEQ><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
+                                                               m_ego, bda, ref_heights, grid, w.run_cnt,
+                                                               w.run_vox, w.run_d, w.hist1);
+  SGV3D_CHECK_LAUNCH("ls_plan_runs_kernel");
+  sort::scan_hist_kernel<<<m.B, sort::kScanThreads, 0, s>>>(w.hist1, sort::kLowBins, m.nchunks, nullptr, 0,
+                                                            w.count);
+  SGV3D_CHECK_LAUNCH("scan_hist_kernel(1)");
+  ls_scatter_ell_kernel<<<gc, kChunk, 0, s>>>(m, w.run_cnt, w.run_vox, w.hist1, w.keys1, w.pay1);
+  SGV3D_CHECK_LAUNCH("ls_scatter_ell_kernel");
+  dim3 g2(m.nblk2, m.B);
+  sort::hist_contiguous_kernel<sort::kLowBits><<<g2, sort::kThreads, sizeof(int) * m.bins2, s>>>(
+      w.keys1, (size_t)m.cap, w.count, 0, m.bins2, m.nblk2, w.hist2);
+  SGV3D_CHECK_LAUNCH("hist_contiguous_kernel");
+  sort::scan_hist_kernel<<<m.B, sort::kScanThreads, 0, s>>>(w.hist2, m.bins2, m.nblk2, w.count,
+                                                            sort::kItemsPerBlock, nullptr);
+  SGV3D_CHECK_LAUNCH("scan_hist_kernel(2)");
+  sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF>
+      <<<g2, sort::kThreads, sizeof(int) * sort::kWarps * m.bins2, s>>>(
+          w.keys1, w.pay1, (size_t)m.cap, w.count, 0, m.bins2, w.hist2, m.nblk2, w.keys2, w.vm_pix,
+          (size_t)m.cap);
+  SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
+  PlanFinalize fin{m, w.vm_pix, w.run_dst};
+  sort::row_ptr_kernel<PlanFinalize><<<dim3(ceil_div(m.cap, 256), m.B), 256, 0, s>>>(
+      w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr, fin);
+  SGV3D_CHECK_LAUNCH("row_ptr_kernel");
+  return SGV3D_OK;
+}
+
+extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const float *height,
+                                        const void *context, float *bev, void *workspace,
+                                        size_t workspace_bytes, sgv3d_stream_t stream) {
+  if (int rc = validate(desc, "lift_splat_forward")) return rc;
+  if (desc->B == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(height && context && bev, "lift_splat_forward: null pointer");
+  const Dims m = make_dims(desc);
+  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
+  dim3 gc(m.nchunks, m.B);
+  ls_weights_kernel<true><<<gc, kChunk, 0, s>>>(m, height, w.run_cnt, w.run_d, w.run_dst, w.w_vm);
+  SGV3D_CHECK_LAUNCH("ls_weights_kernel");
+  if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
+  return launch_reduce<float>(m, w, bev, s);
+}
+
+extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, const float *grad_bev,
+                                         const float *height, const void *context,
+                                         float *grad_height, float *grad_context, void *workspace,
+                                         size_t workspace_bytes, sgv3d_stream_t stream) {
+  if (int rc = validate(desc, "lift_splat_backward")) return rc;
+  if (desc->B == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(grad_bev && height && context && grad_height && grad_context,
+                "lift_splat_backward: null pointer");
+  const Dims m = make_dims(desc);
+  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_backward")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int gpad = ceil_div(m.C, 4) * 4;
+  if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
+  launch_transpose_pad<float, float>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
+                                     (size_t)m.V * gpad, s);
+  SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_bev)");
+  dim3 gc(m.nchunks, m.B);
+  ls_weights_kernel<false><<<gc, kChunk, 0, s>>>(m, height, w.run_cnt, w.run_d, w.run_dst, w.w_pm);
+  SGV3D_CHECK_LAUNCH("ls_weights_kernel");
+  int rc = desc->ctx_dtype == SGV3D_DTYPE_BF16 ? launch_backward_gather<__nv_bfloat16>(m, w, gpad, s)
+                                                : launch_backward_gather<float>(m, w, gpad, s);
+  if (rc) return rc;
+  ls_expand_kernel<false><<<gc, kChunk, 0, s>>>(m, w.run_cnt, w.run_d, w.run_vox, w.gw_pm, grad_height,
+                                                nullptr);
+  SGV3D_CHECK_LAUNCH("ls_expand_kernel");
+  launch_transpose_pad<float, float>(w.gctxT, grad_context, m.B * m.Nc, m.P, m.C, gpad,
+                                     (size_t)m.P * gpad, m.P, (size_t)m.C * m.P, s);
+  SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_context)");
+  return SGV3D_OK;
+}
+
+extern "C" int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, int32_t *vox_out,
+                                            void *workspace, size_t workspace_bytes,
+                                            sgv3d_stream_t stream) {
+  if (int rc = validate(desc, "lift_splat_plan_expand")) return rc;
+  if (desc->B == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(vox_out != nullptr, "lift_splat_plan_expand: null pointer");
+  const Dims m = make_dims(desc);
+  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan_expand")) return rc;
+  dim3 gc(m.nchunks, m.B);
+  ls_expand_kernel<true><<<gc, kChunk, 0, static_cast<cudaStream_t>(stream)>>>(
+      m, w.run_cnt, w.run_d, w.run_vox, nullptr, nullptr, vox_out);
+  SGV3D_CHECK_LAUNCH("ls_expand_kernel(vox)");
+  return SGV3D_OK;
+}

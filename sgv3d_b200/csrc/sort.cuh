@@ -1,0 +1,233 @@
+// Stable per-frame LSD radix sort by voxel id (two passes: low 8 bits, then the remaining high
+// bits), hand-written for sm_100a.  Determinism is the point: ties keep the canonical order in
+// which the producer emitted them, so the per-voxel summation order downstream is fixed and no
+// floating-point atomics are needed (north star: "pre-sorted by voxel rank ... deterministic").
+//
+// Building blocks (all integer work, HBM/L2-bound):
+//   * producers write a per-block digit histogram  hist[frame][bin][block]   (smem int atomics)
+//   * scan_hist_kernel      exclusive scan of that table in bin-major order, one CTA per frame
+//   * radix_scatter_kernel  stable scatter: warp-private running counters + __match_any_sync
+//                           ranking; canonical order inside a block is (warp, iteration, lane)
+#pragma once
+
+#include "common.cuh"
+
+namespace sgv3d {
+namespace sort {
+
+constexpr int kLowBits = 8;
+constexpr int kLowBins = 1 << kLowBits;  // 256
+constexpr int kThreads = 256;            // threads per sort block (8 warps)
+constexpr int kWarps = kThreads / kWarp;
+constexpr int kItemsPerBlock = 2048;     // contiguous items per sort block (256 per warp)
+constexpr int kMaxHighBins = 1024;       // (V >> 8) + 1 <= 1024  =>  V <= 261888 voxels per frame
+constexpr int kScanThreads = 1024;
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan of hist[frame][bin][blk] over (bin-major, blk-minor) for blk < nblk_eff.
+// nblk_eff = nblk_max when n_items == nullptr, else ceil(n_items[frame] / items_per_block).
+// Writes the exclusive prefix in place and the grand total to total_out[frame] (if non-null).
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(kScanThreads)
+scan_hist_kernel(int *__restrict__ hist, int bins, int nblk_max, const int *__restrict__ n_items,
+                 int items_per_block, int *__restrict__ total_out) {
+  __shared__ int warp_tot[kScanThreads / kWarp];
+  __shared__ int carry_s;
+  const int frame = blockIdx.x;
+  int nblk = nblk_max;
+  if (n_items) nblk = (n_items[frame] + items_per_block - 1) / items_per_block;
+  int *h = hist + (size_t)frame * bins * nblk_max;
+  const int L = bins * nblk;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < L; base += kScanThreads) {
+    const int k = base + t;
+    int v = 0;
+    size_t addr = 0;
+    if (k < L) {
+      const int bin = k / nblk, blk = k - bin * nblk;
+      addr = (size_t)bin * nblk_max + blk;
+      v = h[addr];
+    }
+    // inclusive warp scan
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_tot[lane];
+      int xs = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, xs, o);
+        if (lane >= o) xs += y;
+      }
+      warp_tot[lane] = xs - w;  // exclusive prefix of warp totals
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + warp_tot[wid] + x - v;
+    if (k < L) h[addr] = excl;
+    __syncthreads();
+    if (t == kScanThreads - 1) carry_s = excl + v;  // running total after this tile
+    __syncthreads();
+  }
+  if (t == 0 && total_out) total_out[frame] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-block digit histogram of a contiguous key array (used for the second pass, whose input
+// order only exists after the first scatter).
+// ---------------------------------------------------------------------------------------------
+template <int SHIFT>
+__global__ void __launch_bounds__(kThreads)
+hist_contiguous_kernel(const int *__restrict__ keys, size_t frame_stride,
+                       const int *__restrict__ n_items, int n_fixed, int bins, int nblk_max,
+                       int *__restrict__ hist) {
+  extern __shared__ int s_hist[];
+  const int frame = blockIdx.y, blk = blockIdx.x;
+  const int n = n_items ? n_items[frame] : n_fixed;
+  const int begin = blk * kItemsPerBlock;
+  if (begin >= n) return;
+  for (int i = threadIdx.x; i < bins; i += kThreads) s_hist[i] = 0;
+  __syncthreads();
+  const int end = min(n, begin + kItemsPerBlock);
+  const int *k = keys + (size_t)frame * frame_stride;
+  for (int i = begin + threadIdx.x; i < end; i += kThreads) atomicAdd(&s_hist[k[i] >> SHIFT], 1);
+  __syncthreads();
+  int *h = hist + (size_t)frame * bins * nblk_max;
+  for (int i = threadIdx.x; i < bins; i += kThreads) h[(size_t)i * nblk_max + blk] = s_hist[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stable scatter of one sort block.
+//   Input accessor `In` yields, for warp w / iteration it / lane, the item (key, payload, valid)
+//   in canonical order; n_iters(warp) iterations per warp.
+//   gbase = scanned histogram (exclusive, bin-major) for this frame.
+// Phase A: per-warp digit counts (smem int atomics: counts are order independent).
+// Phase B: cross-warp exclusive scan per digit, then match-any ranking with warp-private running
+//          counters => position is a pure function of the canonical order.
+// ---------------------------------------------------------------------------------------------
+template <int NWARPS, typename In, typename DigitFn>
+__device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit_of, int bins,
+                                                     const int *__restrict__ gbase_frame,
+                                                     int nblk_max, int blk, int *s_cnt /*[NWARPS][bins]*/,
+                                                     int *__restrict__ out_keys,
+                                                     int *__restrict__ out_payload) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  for (int i = t; i < NWARPS * bins; i += NWARPS * kWarp) s_cnt[i] = 0;
+  __syncthreads();
+  int *my = s_cnt + wid * bins;
+  const int iters = in.iters(wid);
+  for (int it = 0; it < iters; ++it) {
+    int key, pay;
+    if (in.load(wid, it, lane, key, pay)) atomicAdd(&my[digit_of(key)], 1);
+  }
+  __syncthreads();
+  for (int d = t; d < bins; d += NWARPS * kWarp) {
+    int base = gbase_frame[(size_t)d * nblk_max + blk];
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      const int c = s_cnt[w * bins + d];
+      s_cnt[w * bins + d] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+  const unsigned lt = lanemask_lt();
+  for (int it = 0; it < iters; ++it) {
+    int key = 0, pay = 0;
+    const bool valid = in.load(wid, it, lane, key, pay);
+    // invalid lanes get a private pseudo-digit so that they never match a real one
+    const int dig = valid ? digit_of(key) : (bins + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, dig);
+    const int leader = __ffs(peers) - 1;
+    const int rank = __popc(peers & lt);
+    int base = 0;
+    if (valid && lane == leader) {
+      base = my[dig];
+      my[dig] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) {
+      out_keys[base + rank] = key;
+      out_payload[base + rank] = pay;
+    }
+    __syncwarp();
+  }
+}
+
+// Contiguous input: block `blk` owns items [blk*2048, min(n, (blk+1)*2048)); warp w owns the
+// w-th run of 256 items; payload is either explicit or the item index itself.
+struct ContiguousInput {
+  const int *keys;
+  const int *payload;  // nullptr => payload = item index
+  int begin, n;
+  __device__ __forceinline__ int iters(int) const { return kItemsPerBlock / kWarps / kWarp; }
+  __device__ __forceinline__ bool load(int w, int it, int lane, int &key, int &pay) const {
+    const int i = begin + w * (kItemsPerBlock / kWarps) + it * kWarp + lane;
+    if (i >= n) return false;
+    key = keys[i];
+    pay = payload ? payload[i] : i;
+    return true;
+  }
+};
+
+template <int SHIFT, int MASK>
+struct DigitOf {
+  __device__ __forceinline__ int operator()(int key) const { return (key >> SHIFT) & MASK; }
+};
+
+template <int SHIFT, int MASK>
+__global__ void __launch_bounds__(kThreads)
+scatter_contiguous_kernel(const int *__restrict__ keys_in, const int *__restrict__ payload_in,
+                          size_t frame_stride_in, const int *__restrict__ n_items, int n_fixed,
+                          int bins, const int *__restrict__ gbase, int nblk_max,
+                          int *__restrict__ keys_out, int *__restrict__ payload_out,
+                          size_t frame_stride_out) {
+  extern __shared__ int s_cnt[];
+  const int frame = blockIdx.y, blk = blockIdx.x;
+  const int n = n_items ? n_items[frame] : n_fixed;
+  if (blk * kItemsPerBlock >= n) return;
+  ContiguousInput in{keys_in + (size_t)frame * frame_stride_in,
+                     payload_in ? payload_in + (size_t)frame * frame_stride_in : nullptr,
+                     blk * kItemsPerBlock, n};
+  stable_scatter_block<kWarps>(in, DigitOf<SHIFT, MASK>(), bins,
+                               gbase + (size_t)frame * bins * nblk_max, nblk_max, blk, s_cnt,
+                               keys_out + (size_t)frame * frame_stride_out,
+                               payload_out + (size_t)frame * frame_stride_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// row_ptr[v] = first sorted position whose key >= v, for v in [0, V]; keys sorted ascending.
+// Also applies `fin(j, payload)` per sorted item (used to build the inverse permutation).
+// ---------------------------------------------------------------------------------------------
+template <typename Fin>
+__global__ void __launch_bounds__(256)
+row_ptr_kernel(const int *__restrict__ keys, size_t frame_stride, const int *__restrict__ n_items,
+               int n_fixed, int V, int *__restrict__ row_ptr /*[frame][V+1]*/, Fin fin) {
+  const int frame = blockIdx.y;
+  const int n = n_items ? n_items[frame] : n_fixed;
+  const int *k = keys + (size_t)frame * frame_stride;
+  int *rp = row_ptr + (size_t)frame * (V + 1);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0) {
+    for (int v = j; v <= V; v += gridDim.x * blockDim.x) rp[v] = 0;
+    return;
+  }
+  if (j >= n) return;
+  const int key = min(k[j], V);
+  const int prev = (j > 0) ? min(k[j - 1], V) : -1;
+  for (int v = prev + 1; v <= key; ++v) rp[v] = j;
+  if (j == n - 1)
+    for (int v = key + 1; v <= V; ++v) rp[v] = n;
+  fin(frame, j);
+}
+
+}  // namespace sort
+}  // namespace sgv3d

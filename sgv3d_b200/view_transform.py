@@ -1,0 +1,300 @@
+"""Host side of the fused lift-splat: plan / forward / backward over the C ABI, plus a module that
+mirrors the view-transform half of the reference's ``LSSFPN`` / ``BSMLSSFPN``.
+
+Reference call sites (relative to the reference repository root):
+  layers/backbones/lss_fpn.py:462-495       LSSFPN._forward_single_sweep (after the height net)
+  layers/backbones/bsm_lss_fpn.py:523-559   BSMLSSFPN._forward_single_sweep
+  layers/backbones/lss_fpn.py:281-294       registered buffers (voxel_size/coord/num, frustum)
+  layers/backbones/lss_fpn.py:325-401       create_frustum / height2localtion / get_geometry
+
+The per-camera 4x4 products are kept in PyTorch with the same calls as the reference so the 16
+floats per matrix that enter the per-point arithmetic are identical (SURVEY.md §7 hard part 1);
+everything per point / per pixel / per voxel happens in the sm_100a kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _native as N
+
+__all__ = ["camera_matrices", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat",
+           "build_frustum", "default_arith"]
+
+_DEFAULT_ARITH = N.ARITH_SEQ
+
+
+def default_arith() -> int:
+    """Evaluation order used for the per-point dot products unless overridden.  SEQ reproduces the
+    reference executed on CPU bit for bit; see DESIGN.md for what cuBLAS does on B200."""
+    return _DEFAULT_ARITH
+
+
+def set_default_arith(arith: int) -> None:
+    global _DEFAULT_ARITH
+    assert arith in (N.ARITH_SEQ, N.ARITH_FMA)
+    _DEFAULT_ARITH = arith
+
+
+def build_frustum(final_dim: Sequence[int], downsample_factor: int, d_bound: Sequence[float]) -> torch.Tensor:
+    """(D, fH, fW, 4) fp32 buffer of (u, v, z_d, 1) -- same values as ``LSSFPN.create_frustum``
+    (lss_fpn.py:325-348): torch fp32 ``linspace`` pixel centres and the float64 "DID" height bins
+    z_d = d0 + (d/D)^1.5 (d1 - d0) cast to fp32."""
+    in_h, in_w = final_dim
+    f_h, f_w = in_h // downsample_factor, in_w // downsample_factor
+    n_bins = int(d_bound[2])
+    z = d_bound[0] + np.power(np.arange(n_bins) / n_bins, 1.5) * (d_bound[1] - d_bound[0])
+    z = torch.tensor(z, dtype=torch.float).view(n_bins, 1, 1).expand(n_bins, f_h, f_w)
+    u = torch.linspace(0, in_w - 1, f_w, dtype=torch.float).view(1, 1, f_w).expand(n_bins, f_h, f_w)
+    v = torch.linspace(0, in_h - 1, f_h, dtype=torch.float).view(1, f_h, 1).expand(n_bins, f_h, f_w)
+    return torch.stack((u, v, z, torch.ones_like(z)), -1)
+
+
+def camera_matrices(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat):
+    """``ida.inverse()``, ``sensor2virtual @ inverse(intrin)``, ``sensor2ego @ inverse(sensor2virtual)``
+    evaluated with the reference's own torch calls (lss_fpn.py:392,361,367), shapes (B, Nc, 4, 4)."""
+    ida_inv = ida_mat.inverse()
+    m_virtual = sensor2virtual_mat.matmul(torch.inverse(intrin_mat))
+    m_ego = sensor2ego_mat.matmul(torch.inverse(sensor2virtual_mat))
+    return ida_inv, m_virtual, m_ego
+
+
+def _f32c(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class _Geometry:
+    """Device-resident operands of the per-point geometry for one batch of cameras."""
+
+    def __init__(self, frustum, sensor2ego, sensor2virtual, intrin, ida, reference_heights, bda,
+                 voxel_coord, voxel_size):
+        dev = sensor2ego.device
+        if dev.type != "cuda":
+            raise RuntimeError("sgv3d_b200 runs on CUDA tensors only (no CPU fallback)")
+        self.device = dev
+        self.B, self.Nc = int(sensor2ego.shape[0]), int(sensor2ego.shape[1])
+        self.D, self.fH, self.fW = (int(s) for s in frustum.shape[:3])
+        fr = frustum.to(dev)
+        # the three axes of the frustum buffer; looked up, never recomputed
+        self.u = fr[0, 0, :, 0].contiguous()
+        self.v = fr[0, :, 0, 1].contiguous()
+        self.z = fr[:, 0, 0, 2].contiguous()
+        ida_inv, m_virtual, m_ego = camera_matrices(sensor2ego, sensor2virtual, intrin, ida)
+        self.ida_inv, self.m_virtual, self.m_ego = (_f32c(t, dev) for t in (ida_inv, m_virtual, m_ego))
+        self.ref_h = _f32c(reference_heights, dev).reshape(-1)
+        self.bda = _f32c(bda, dev)
+        # lss_fpn.py:487-488: lower = voxel_coord - voxel_size / 2.0 in fp32 tensor arithmetic
+        vc, vs = voxel_coord.detach().float().cpu(), voxel_size.detach().float().cpu()
+        self.lower = N.host_f32x3((vc - vs / 2.0).tolist())
+        self.size = N.host_f32x3(vs.tolist())
+
+    def pointer_args(self):
+        return [N.ptr(self.u), N.ptr(self.v), N.ptr(self.z), N.ptr(self.ida_inv), N.ptr(self.m_virtual),
+                N.ptr(self.m_ego), N.ptr(self.bda), N.ptr(self.ref_h), self.lower, self.size]
+
+
+def geometry_indices(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
+                     bda_mat, voxel_coord, voxel_size, arith: Optional[int] = None, return_xyz: bool = False):
+    """int32 (B, Nc, D, fH, fW, 3) voxel indices == ``((get_geometry(...) - lower) / size).int()``
+    (lss_fpn.py:478-488), computed by one kernel; optionally also the fp32 ego coordinates."""
+    g = _Geometry(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
+                  bda_mat, voxel_coord, voxel_size)
+    idx = torch.empty(g.B, g.Nc, g.D, g.fH, g.fW, 3, dtype=torch.int32, device=g.device)
+    xyz = torch.empty(idx.shape, dtype=torch.float32, device=g.device) if return_xyz else None
+    with torch.cuda.device(g.device):
+        N.check(N.lib().sgv3d_geometry_quantize(
+            default_arith() if arith is None else arith, g.B, g.Nc, g.D, g.fH, g.fW, *g.pointer_args(),
+            N.ptr(idx), N.ptr(xyz), N.current_stream()))
+    return (idx, xyz) if return_xyz else idx
+
+
+class LiftSplatPlan:
+    """Sorted voxel-run index for one batch of calibrations (``sgv3d_lift_splat_plan``).
+
+    Depends only on the matrices and the grid, so a static roadside camera can build it once and
+    reuse it for every frame; in training it is rebuilt per step."""
+
+    def __init__(self, frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
+                 bda_mat, voxel_coord, voxel_size, voxel_num: Sequence[int], channels: int,
+                 ctx_dtype: torch.dtype = torch.float32, arith: Optional[int] = None):
+        g = _Geometry(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
+                      bda_mat, voxel_coord, voxel_size)
+        self.geometry = g
+        self.device = g.device
+        if ctx_dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"context dtype {ctx_dtype} unsupported (float32 or bfloat16)")
+        self.ctx_dtype = ctx_dtype
+        nx, ny, nz = (int(v) for v in voxel_num)
+        self.desc = N.LiftSplatDesc(B=g.B, Nc=g.Nc, D=g.D, fH=g.fH, fW=g.fW, C=int(channels), X=nx, Y=ny, Z=nz,
+                                    arith=default_arith() if arith is None else arith,
+                                    ctx_dtype=N.DTYPE_BF16 if ctx_dtype == torch.bfloat16 else N.DTYPE_F32)
+        L = N.lib()
+        self.ws_bytes = L.sgv3d_lift_splat_workspace_bytes(self.desc)
+        if g.B > 0 and self.ws_bytes == 0:
+            N.check(1)
+        self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=g.device)
+        self.rebuild()
+
+    def rebuild(self) -> None:
+        g = self.geometry
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sgv3d_lift_splat_plan(self.desc, *g.pointer_args(), N.ptr(self.ws), self.ws_bytes,
+                                                  N.current_stream()))
+
+    # -- raw entry points (no autograd) -------------------------------------------------------------
+    def forward(self, height: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        d = self.desc
+        self._check_inputs(height, context)
+        bev = torch.empty(d.B, d.C, d.Y, d.X, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sgv3d_lift_splat_forward(d, N.ptr(height), N.ptr(context), N.ptr(bev), N.ptr(self.ws),
+                                                     self.ws_bytes, N.current_stream()))
+        return bev
+
+    def backward(self, grad_bev: torch.Tensor, height: torch.Tensor, context: torch.Tensor):
+        d = self.desc
+        self._check_inputs(height, context)
+        g = grad_bev.float().contiguous()
+        assert g.shape == (d.B, d.C, d.Y, d.X)
+        g_height = torch.empty_like(height)
+        g_ctx = torch.empty(context.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sgv3d_lift_splat_backward(d, N.ptr(g), N.ptr(height), N.ptr(context), N.ptr(g_height),
+                                                      N.ptr(g_ctx), N.ptr(self.ws), self.ws_bytes,
+                                                      N.current_stream()))
+        return g_height, g_ctx
+
+    def expand(self) -> torch.Tensor:
+        """int32 (B, Nc, D, fH, fW): voxel id y*X+x per point, -1 for dropped points (parity/debug)."""
+        d = self.desc
+        vox = torch.empty(d.B, d.Nc, d.D, d.fH, d.fW, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sgv3d_lift_splat_plan_expand(d, N.ptr(vox), N.ptr(self.ws), self.ws_bytes,
+                                                         N.current_stream()))
+        return vox
+
+    def _check_inputs(self, height, context):
+        d = self.desc
+        bn = d.B * d.Nc
+        if not (height.is_cuda and context.is_cuda):
+            raise RuntimeError("height and context must be CUDA tensors")
+        assert height.is_contiguous() and context.is_contiguous()
+        if height.dtype != torch.float32:
+            raise RuntimeError(f"expected height of dtype float32, got {height.dtype}")
+        if context.dtype != self.ctx_dtype:
+            raise RuntimeError(f"expected context of dtype {self.ctx_dtype}, got {context.dtype}")
+        assert tuple(height.shape) == (bn, d.D, d.fH, d.fW), (tuple(height.shape), (bn, d.D, d.fH, d.fW))
+        assert tuple(context.shape) == (bn, d.C, d.fH, d.fW), (tuple(context.shape), (bn, d.C, d.fH, d.fW))
+
+
+class _LiftSplatFunction(Function):
+    @staticmethod
+    def forward(ctx, height, context, plan: LiftSplatPlan):
+        height = height.contiguous()
+        context = context.contiguous()
+        ctx.plan = plan
+        ctx.save_for_backward(height, context)
+        return plan.forward(height, context)
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        height, context = ctx.saved_tensors
+        g_height, g_ctx = ctx.plan.backward(grad_bev, height, context)
+        return g_height, g_ctx.to(context.dtype), None
+
+
+def lift_splat(height: torch.Tensor, context: torch.Tensor, plan: LiftSplatPlan) -> torch.Tensor:
+    """(B, C, Y, X) fp32 contiguous BEV map: ``voxel_pooling(idx, (height (x) context) permuted)``
+    of lss_fpn.py:464-495 without the frustum tensor.  Differentiable w.r.t. height and context."""
+    return _LiftSplatFunction.apply(height, context, plan)
+
+
+class LiftSplat(nn.Module):
+    """View-transform half of ``LSSFPN`` / ``BSMLSSFPN``: same constructor keys, same registered
+    buffers (so ``state_dict`` entries line up with lss_fpn.py:281-293), same per-sweep maths.
+
+    ``forward_single_sweep`` consumes what the height net produced and returns what
+    ``_forward_single_sweep`` returns for the BEV map (lss_fpn.py:494-495)."""
+
+    def __init__(self, x_bound, y_bound, z_bound, d_bound, final_dim, downsample_factor, output_channels,
+                 is_bsm: bool = False, arith: Optional[int] = None, cache_plan: bool = False):
+        super().__init__()
+        # BSMLSSFPN halves the stride of the lifted feature map (bsm_lss_fpn.py:343)
+        self.downsample_factor = downsample_factor // 2 if is_bsm else downsample_factor
+        self.is_bsm = is_bsm
+        self.d_bound = list(d_bound)
+        self.final_dim = tuple(final_dim)
+        self.output_channels = output_channels
+        self.arith = arith
+        self.cache_plan = cache_plan
+        rows = [x_bound, y_bound, z_bound]
+        self.register_buffer("voxel_size", torch.Tensor([r[2] for r in rows]))
+        self.register_buffer("voxel_coord", torch.Tensor([r[0] + r[2] / 2.0 for r in rows]))
+        self.register_buffer("voxel_num", torch.LongTensor([(r[1] - r[0]) / r[2] for r in rows]))
+        self.register_buffer("frustum", build_frustum(self.final_dim, self.downsample_factor, self.d_bound))
+        self.height_channels = int(self.frustum.shape[0])
+        # host copies, so that no call has to read a CUDA scalar (lss_fpn.py:491 syncs every call)
+        self._grid = tuple(int(v) for v in self.voxel_num.tolist())
+        self._plan_cache: Dict[tuple, LiftSplatPlan] = {}
+
+    # -- geometry -----------------------------------------------------------------------------------
+    def get_geometry(self, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights, bda_mat):
+        """fp32 (B, Nc, D, fH, fW, 3) ego-frame points, as ``LSSFPN.get_geometry`` (lss_fpn.py:372-401)."""
+        _, xyz = geometry_indices(self.frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat,
+                                  reference_heights, bda_mat, self.voxel_coord, self.voxel_size, self.arith,
+                                  return_xyz=True)
+        return xyz
+
+    def get_geometry_indices(self, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
+                             bda_mat):
+        """int32 voxel indices of lss_fpn.py:487-488."""
+        return geometry_indices(self.frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat,
+                                reference_heights, bda_mat, self.voxel_coord, self.voxel_size, self.arith)
+
+    def make_plan(self, mats_dict, sweep_index: int = 0, channels: Optional[int] = None,
+                  ctx_dtype: torch.dtype = torch.float32) -> LiftSplatPlan:
+        m = mats_dict
+        args = (m["sensor2ego_mats"][:, sweep_index, ...], m["sensor2virtual_mats"][:, sweep_index, ...],
+                m["intrin_mats"][:, sweep_index, ...], m["ida_mats"][:, sweep_index, ...],
+                m["reference_heights"][:, sweep_index, ...], m.get("bda_mat", None))
+        c = channels or self.output_channels
+        key = None
+        if self.cache_plan:
+            key = (c, ctx_dtype) + tuple(None if a is None else (a.data_ptr(), a._version, tuple(a.shape))
+                                         for a in args)
+            if key in self._plan_cache:
+                return self._plan_cache[key]
+        plan = LiftSplatPlan(self.frustum, *args, self.voxel_coord, self.voxel_size, self._grid, c, ctx_dtype,
+                             self.arith)
+        if key is not None:
+            self._plan_cache = {key: plan}
+        return plan
+
+    # -- call sites ---------------------------------------------------------------------------------
+    def forward_single_sweep(self, height_feature: torch.Tensor, mats_dict, sweep_index: int = 0) -> torch.Tensor:
+        """LSSFPN: ``height_feature`` = (B*Nc, D + C, fH, fW) output of the height net
+        (lss_fpn.py:461).  Returns the (B, C, Y, X) contiguous BEV map of lss_fpn.py:494-495."""
+        d, c = self.height_channels, self.output_channels
+        height = height_feature[:, :d].softmax(1)                               # lss_fpn.py:462
+        context = height_feature[:, d:d + c]                                    # lss_fpn.py:464-466
+        plan = self.make_plan(mats_dict, sweep_index, c)
+        return lift_splat(height.float(), context.float(), plan)
+
+    def forward_single_sweep_bsm(self, height_logits, semantic_logits, context, mats_dict,
+                                 sweep_index: int = 0) -> torch.Tensor:
+        """BSMLSSFPN: ``out[0], out[1], out[2]`` of the MSCT head (bsm_lss_fpn.py:522-529): height
+        logits (BN, D, fH, fW), 7 semantic logits, 80 context channels.  The 87-channel masked context
+        is assembled exactly as the reference does, then lifted and splatted."""
+        height = height_logits.softmax(dim=1)                                   # bsm_lss_fpn.py:523
+        semantic = semantic_logits.softmax(dim=1)                               # :524
+        tran_feat = torch.cat((context, semantic), dim=1)                       # :526
+        mask = semantic[:, 0, :, :].unsqueeze(1) > 0.45                         # :528 background
+        tran_feat = tran_feat * (1 - mask.int())                                # :529
+        plan = self.make_plan(mats_dict, sweep_index, int(tran_feat.shape[1]))
+        return lift_splat(height.float(), tran_feat.float(), plan)
