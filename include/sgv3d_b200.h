@@ -50,9 +50,13 @@ extern "C" {
  * (torch.matmul -> bmm at lss_fpn.py:361-362,367-369,392,398):
  *   SEQ: ((a0*b0 + a1*b1) + a2*b2) + a3*b3, every product and sum rounded to fp32
  *        (what torch's CPU bmm does; bit-exact with the reference run on CPU)
- *   FMA: fma(a3,b3, fma(a2,b2, fma(a1,b1, a0*b0)))  (k-ascending FMA chain) */
+ *   FMA: fma(a3,b3, fma(a2,b2, fma(a1,b1, a0*b0)))  (k-ascending FMA chain)
+ *   PAIR: fma(a1,b1, a0*b0) + fma(a3,b3, a2*b2)     (pairwise FMA: what torch's CUDA bmm -> cuBLAS
+ *        does for these shapes on B200, i.e. bit-exact with the reference run on the GPU; measured
+ *        by tools/probe_arith.py, see profiles/arith_probe_r01.json) */
 #define SGV3D_ARITH_SEQ 0
 #define SGV3D_ARITH_FMA 1
+#define SGV3D_ARITH_PAIR 2
 
 /* element type of the context tensor handed to sgv3d_lift_splat_forward/backward */
 #define SGV3D_DTYPE_F32 0

@@ -18,6 +18,7 @@ _REF = os.path.join(_HERE, "_ref", "libvoxel_pooling_ref.so")
 
 ARITH_SEQ = 0  # torch-CPU order: separately rounded mul / add
 ARITH_FMA = 1  # k-ascending FMA chain
+ARITH_PAIR = 2  # fma(a1,b1,a0*b0) + fma(a3,b3,a2*b2): torch CUDA bmm (cuBLAS) on B200
 
 _f = ctypes.POINTER(ctypes.c_float)
 _d = ctypes.POINTER(ctypes.c_double)

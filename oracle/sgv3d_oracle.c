@@ -27,13 +27,21 @@
  * (lss_fpn.py:361-362,367-369,392,398 -- torch.matmul -> bmm):
  *   ORACLE_ARITH_SEQ : ((a0*b0 + a1*b1) + a2*b2) + a3*b3, every mul and add rounded
  *                      (what torch CPU bmm does for these shapes -- SURVEY.md §7 hard part 1)
- *   ORACLE_ARITH_FMA : fma(a3,b3, fma(a2,b2, fma(a1,b1, a0*b0)))  (k-ascending FMA chain,
- *                      the candidate order for cuBLAS on the GPU; pinned empirically on B200)
+ *   ORACLE_ARITH_FMA : fma(a3,b3, fma(a2,b2, fma(a1,b1, a0*b0)))  (k-ascending FMA chain)
+ *   ORACLE_ARITH_PAIR: fma(a1,b1, a0*b0) + fma(a3,b3, a2*b2)      (pairwise FMA: what torch's CUDA
+ *                      bmm / cuBLAS does for these shapes on B200 -- 0 bit mismatches over
+ *                      4 x 3.7M outputs per stage, tools/probe_arith.py, profiles/arith_probe_r01.json)
  */
 #define ORACLE_ARITH_SEQ 0
 #define ORACLE_ARITH_FMA 1
+#define ORACLE_ARITH_PAIR 2
 
 static inline float dot4(int mode, const float *a, float b0, float b1, float b2, float b3) {
+  if (mode == ORACLE_ARITH_PAIR) {
+    const float lo = fmaf(a[1], b1, a[0] * b0);
+    const float hi = fmaf(a[3], b3, a[2] * b2);
+    return lo + hi;
+  }
   if (mode == ORACLE_ARITH_FMA) {
     float acc = a[0] * b0;
     acc = fmaf(a[1], b1, acc);

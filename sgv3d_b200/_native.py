@@ -12,7 +12,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsgv3d_b200.so")
 
-ARITH_SEQ, ARITH_FMA = 0, 1
+ARITH_SEQ, ARITH_FMA, ARITH_PAIR = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ABI_VERSION = 1
 

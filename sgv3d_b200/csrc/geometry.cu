@@ -58,7 +58,7 @@ extern "C" int sgv3d_geometry_quantize(int arith, int B, int Nc, int D, int fH, 
                                        sgv3d_stream_t stream) {
   using namespace sgv3d;
   SGV3D_REQUIRE(B >= 0 && Nc > 0 && D > 0 && fH > 0 && fW > 0, "geometry_quantize: bad sizes");
-  SGV3D_REQUIRE(arith == SGV3D_ARITH_SEQ || arith == SGV3D_ARITH_FMA, "geometry_quantize: bad arith %d", arith);
+  SGV3D_REQUIRE(arith >= SGV3D_ARITH_SEQ && arith <= SGV3D_ARITH_PAIR, "geometry_quantize: bad arith %d", arith);
   SGV3D_REQUIRE(u_tab && v_tab && z_tab && ida_inv && m_virtual && m_ego && ref_heights && lower3 && size3,
                 "geometry_quantize: null pointer");
   SGV3D_REQUIRE((long long)B * Nc <= 65535, "geometry_quantize: B*Nc > 65535");
@@ -69,7 +69,10 @@ extern "C" int sgv3d_geometry_quantize(int arith, int B, int Nc, int D, int fH, 
   dim3 g(ceil_div(fH * fW, kThreads), B * Nc);
   const size_t smem = sizeof(float) * D;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (arith == SGV3D_ARITH_FMA)
+  if (arith == SGV3D_ARITH_PAIR)
+    geometry_quantize_kernel<SGV3D_ARITH_PAIR><<<g, kThreads, smem, s>>>(
+        Nc, D, fH, fW, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda, ref_heights, grid, idx_out, xyz_out);
+  else if (arith == SGV3D_ARITH_FMA)
     geometry_quantize_kernel<SGV3D_ARITH_FMA><<<g, kThreads, smem, s>>>(
         Nc, D, fH, fW, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda, ref_heights, grid, idx_out, xyz_out);
   else

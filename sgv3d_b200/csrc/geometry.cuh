@@ -35,6 +35,11 @@ struct Grid {
 
 template <int ARITH>
 __device__ __forceinline__ float dot4(const float *m, float b0, float b1, float b2, float b3) {
+  if (ARITH == SGV3D_ARITH_PAIR) {
+    const float lo = __fmaf_rn(m[1], b1, __fmul_rn(m[0], b0));
+    const float hi = __fmaf_rn(m[3], b3, __fmul_rn(m[2], b2));
+    return __fadd_rn(lo, hi);
+  }
   float acc = __fmul_rn(m[0], b0);
   if (ARITH == SGV3D_ARITH_FMA) {
     acc = __fmaf_rn(m[1], b1, acc);
@@ -48,16 +53,17 @@ __device__ __forceinline__ float dot4(const float *m, float b0, float b1, float 
   return acc;
 }
 
-// first two terms of a row: m0*b0 (+) m1*b1
+// first two terms of a row: m0*b0 (+) m1*b1  (identical sub-expression in all three orders' heads)
 template <int ARITH>
 __device__ __forceinline__ float dot2_head(const float *m, float b0, float b1) {
   float acc = __fmul_rn(m[0], b0);
-  if (ARITH == SGV3D_ARITH_FMA) return __fmaf_rn(m[1], b1, acc);
-  return __fadd_rn(acc, __fmul_rn(m[1], b1));
+  if (ARITH == SGV3D_ARITH_SEQ) return __fadd_rn(acc, __fmul_rn(m[1], b1));
+  return __fmaf_rn(m[1], b1, acc);
 }
 // remaining two terms: (+) m2*b2 (+) m3*b3
 template <int ARITH>
 __device__ __forceinline__ float dot2_tail(float acc, const float *m, float b2, float b3) {
+  if (ARITH == SGV3D_ARITH_PAIR) return __fadd_rn(acc, __fmaf_rn(m[3], b3, __fmul_rn(m[2], b2)));
   if (ARITH == SGV3D_ARITH_FMA) {
     acc = __fmaf_rn(m[2], b2, acc);
     return __fmaf_rn(m[3], b3, acc);

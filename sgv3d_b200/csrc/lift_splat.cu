@@ -498,7 +498,7 @@ int validate(const sgv3d_lift_splat_desc *d, const char *who) {
   SGV3D_REQUIRE(d->C <= 256, "%s: C=%d > 256 unsupported by the fused path", who, d->C);
   SGV3D_REQUIRE((long long)d->X * d->Y < (long long)sort::kMaxHighBins << sort::kLowBits,
                 "%s: X*Y exceeds %d voxels per frame", who, sort::kMaxHighBins << sort::kLowBits);
-  SGV3D_REQUIRE(d->arith == SGV3D_ARITH_SEQ || d->arith == SGV3D_ARITH_FMA, "%s: bad arith", who);
+  SGV3D_REQUIRE(d->arith >= SGV3D_ARITH_SEQ && d->arith <= SGV3D_ARITH_PAIR, "%s: bad arith", who);
   SGV3D_REQUIRE(d->ctx_dtype == SGV3D_DTYPE_F32 || d->ctx_dtype == SGV3D_DTYPE_BF16, "%s: bad ctx_dtype", who);
   const long long slots = (long long)d->Nc * ceil_div(d->fH * d->fW, kChunk) * kChunk * d->D;
   SGV3D_REQUIRE(slots < (1ll << 31), "%s: more than 2^31 height-bin slots per frame", who);
@@ -586,7 +586,11 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
 
   dim3 gc(m.nchunks, m.B);
   const size_t zsm = sizeof(float) * m.D;
-  if (desc->arith == SGV3D_ARITH_FMA)
+  if (desc->arith == SGV3D_ARITH_PAIR)
+    ls_plan_runs_kernel<SGV3D_ARITH_PAIR><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
+                                                                m_ego, bda, ref_heights, grid, w.run_cnt,
+                                                                w.run_vox, w.run_d, w.hist1);
+  else if (desc->arith == SGV3D_ARITH_FMA)
     ls_plan_runs_kernel<SGV3D_ARITH_FMA><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
                                                                m_ego, bda, ref_heights, grid, w.run_cnt,
                                                                w.run_vox, w.run_d, w.hist1);

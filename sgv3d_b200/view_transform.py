@@ -25,18 +25,19 @@ from . import _native as N
 __all__ = ["camera_matrices", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat",
            "build_frustum", "default_arith"]
 
-_DEFAULT_ARITH = N.ARITH_SEQ
+_DEFAULT_ARITH = N.ARITH_PAIR
 
 
 def default_arith() -> int:
-    """Evaluation order used for the per-point dot products unless overridden.  SEQ reproduces the
-    reference executed on CPU bit for bit; see DESIGN.md for what cuBLAS does on B200."""
+    """Evaluation order used for the per-point dot products unless overridden.
+    PAIR (default) reproduces the reference executed on the GPU (torch CUDA ``matmul`` -> cuBLAS bmm on
+    B200) bit for bit; SEQ reproduces the reference executed on CPU.  See DESIGN.md §3."""
     return _DEFAULT_ARITH
 
 
 def set_default_arith(arith: int) -> None:
     global _DEFAULT_ARITH
-    assert arith in (N.ARITH_SEQ, N.ARITH_FMA)
+    assert arith in (N.ARITH_SEQ, N.ARITH_FMA, N.ARITH_PAIR)
     _DEFAULT_ARITH = arith
 
 

@@ -44,7 +44,7 @@ def _mats(shape, batch, num_cams, seed, bda):
             "ida": m["ida"], "reference_heights": m["reference_heights"], "bda": m["bda"]}
 
 
-@pytest.mark.parametrize("arith,mode", [(0, CO.ARITH_SEQ), (1, CO.ARITH_FMA)])
+@pytest.mark.parametrize("arith,mode", [(0, CO.ARITH_SEQ), (1, CO.ARITH_FMA), (2, CO.ARITH_PAIR)])
 @pytest.mark.parametrize("shape_name,batch,num_cams,bda", [
     ("tiny", 2, 2, None), ("small", 3, 1, "random"), ("dair_r50", 2, 1, "identity"),
     ("rope3d_r50", 1, 1, "random"), ("rope3d_native", 1, 1, "identity"), ("sgv3d_bsm_r50", 1, 1, "identity"),
@@ -99,8 +99,32 @@ def test_degenerate_rays_follow_gpu_cast_semantics():
     mats["intrin"] = k.view(1, 1, 4, 4).clone()
     mats["ida"] = torch.eye(4).view(1, 1, 4, 4).clone()
     dev = {kk: (vv.cuda() if vv is not None else None) for kk, vv in mats.items()}
-    for arith, mode in ((0, CO.ARITH_SEQ), (1, CO.ARITH_FMA)):
+    for arith, mode in ((0, CO.ARITH_SEQ), (1, CO.ARITH_FMA), (2, CO.ARITH_PAIR)):
         idx_o, _ = _oracle(shape, mats, mode, device_mats=dev)
         idx_k, _ = _run_kernel(shape, mats, arith)
         assert np.array_equal(idx_k, idx_o)
-    assert (idx_o == np.iinfo(np.int32).max).any() or (idx_o == np.iinfo(np.int32).min).any()
+    # the v = 0 feature row: 0 * inf = NaN in every coordinate -> index (0, 0, 0), i.e. KEPT in voxel 0
+    assert (idx_o[0, 0, :, 0] == 0).all() and (idx_o[0, 0, :, 1:, :, 0] != 0).any()
+
+
+@pytest.mark.parametrize("shape_name,batch,bda", [("dair_r50", 2, "identity"), ("rope3d_r50", 2, "random"),
+                                                  ("sgv3d_bsm_r50", 1, "identity"), ("small", 4, None)])
+def test_default_arith_matches_reference_port_on_the_gpu(shape_name, batch, bda):
+    """The device oracle: the torch port of get_geometry (same calls, same broadcast shapes as
+    lss_fpn.py:350-401) executed ON THE GPU, i.e. what the reference computes in production
+    (cuBLAS bmm).  Default arithmetic (PAIR) must reproduce its indices and coordinates bit for bit."""
+    from sgv3d_b200.view_transform import default_arith, geometry_indices
+    from sgv3d_b200 import _native as N
+    assert default_arith() == N.ARITH_PAIR
+    shape = get_shape(shape_name)
+    mats = _mats(shape, batch, 1, seed=91, bda=bda)
+    dev = {k: (v.cuda() if v is not None else None) for k, v in mats.items()}
+    fr = oracle_frustum(shape)
+    vs, vc, _ = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    geom = O.geometry_matmul(fr.cuda(), dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"],
+                             dev["reference_heights"], dev["bda"])
+    idx_ref = O.quantize(geom, vc.cuda(), vs.cuda())
+    idx, xyz = geometry_indices(fr, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"],
+                                dev["reference_heights"], dev["bda"], vc, vs, return_xyz=True)
+    assert int((idx != idx_ref).any(-1).sum()) == 0
+    assert torch.equal(xyz.view(torch.int32), geom.contiguous().view(torch.int32))

@@ -107,7 +107,7 @@ def main():
         rep["points"] = int(idx_dev.size // 3)
         rep["torch_cuda_vs_torch_cpu_idx_points_differ"] = int((idx_dev != idx_cpu).any(-1).sum())
         from sgv3d_b200.view_transform import geometry_indices
-        for arith, nm in ((0, "SEQ"), (1, "FMA")):
+        for arith, nm in ((0, "SEQ"), (1, "FMA"), (2, "PAIR")):
             idx_k, xyz_k = geometry_indices(frd, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"],
                                             dev["reference_heights"], dev["bda"], vc, vs, arith=arith, return_xyz=True)
             rep[f"kernel_{nm}_vs_torch_cuda_idx_points_differ"] = int((idx_k.cpu().numpy() != idx_dev).any(-1).sum())
