@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- lift-splat frames/s + achieved HBM GB/s vs the B200 roofline, beside a CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--shape NAME]
+
+One "step" = one pass of the hot path (height softmax -> per-frame geometry + voxel-run plan ->
+fused BEV reduction) over one batch of B synthetic frames per GPU, every frame with its own
+calibration (so the geometry is recomputed every step, as in training / multi-site inference).
+For N > 1 launch through ``python -m torch.distributed.run`` (one rank per GPU); frames are
+sharded across ranks, there is no collective on the data path ("replicas only").
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU restatement of the reference path
+(oracle/lift_splat_oracle.py: the reference's geometry calls + torch-CPU index_add_) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from sgv3d_b200.shapes import get_shape  # noqa: E402
+from sgv3d_b200.synthetic import make_activations, make_mats  # noqa: E402
+
+METRIC = "lift_splat_frames_per_sec"
+UNIT = "frames/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _mats_dict(mats, device):
+    return {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).to(device),
+            "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).to(device),
+            "intrin_mats": mats["intrin"].unsqueeze(1).to(device),
+            "ida_mats": mats["ida"].unsqueeze(1).to(device),
+            "reference_heights": mats["reference_heights"].unsqueeze(1).to(device),
+            "bda_mat": mats["bda"].to(device) if mats.get("bda") is not None else None}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING a timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].strip().lower() == "active":
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(shape, frames: int, warmup: int, budget_s: float = 40.0):
+    """Times the CPU restatement of the reference forward path (1 frame per call).
+    Returns (frames_per_s, frames_timed, cores)."""
+    from oracle import lift_splat_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fr = O.create_frustum(shape.final_dim, shape.downsample, shape.d_bound)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + frames):
+        mats = make_mats(shape, 1, 1, seed=1000 + i, bda="identity")
+        logits, ctx = make_activations(shape, 1, 1, seed=i)
+        t0 = time.perf_counter()
+        bev, _, _ = O.lift_splat_forward(logits, ctx, fr, mats, vc, vs, vn)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    total = sum(times)
+    return len(times) / total, len(times), cores, total
+
+
+def run_reference(args):
+    rank, world, _ = _dist()
+    if rank != 0:
+        return
+    shape = get_shape(args.shape)
+    fps, n, cores, total = cpu_reference_run(shape, args.steps, max(args.warmup, 1), budget_s=150.0)
+    sample = f"{n} frame(s) of {shape.name}, 1 frame per step, torch-CPU port of the reference path"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / n, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{shape.name} lift-splat forward (softmax + get_geometry + lift + index_add_ pooling) on CPU",
+                   "frames_per_step": 1, "shape": shape.name},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, world, local = _dist()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    from sgv3d_b200 import LiftSplat, _native as N
+    shape = get_shape(args.shape)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                    shape.downsample, shape.channels).to(dev)
+    # two rotating input sets, each far larger than L2 together with the output
+    nsets = 2
+    sets = []
+    for i in range(nsets):
+        seed = 10_000 * rank + i
+        mats = make_mats(shape, B, 1, seed=seed, bda="identity")
+        logits, ctx = make_activations(shape, B, 1, seed=seed, device=dev, generator_device=dev)
+        hf = torch.cat((logits, ctx), 1).contiguous()
+        sets.append((hf, _mats_dict(mats, dev), mats))
+    in_bytes = sets[0][0].numel() * 4
+    out_bytes = B * shape.channels * shape.grid[0] * shape.grid[1] * 4
+
+    def step(i):
+        hf, md, _ = sets[i % nsets]
+        with torch.no_grad():
+            return mod.forward_single_sweep(hf, md)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    N.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = N.launch_count(reset=True)
+    clocks = sampler.stop()
+
+    # ---- per-kernel durations (CUDA events inside the library, same loop) -------------------------
+    N.profile_enable(True)
+    N.profile_report()
+    for i in range(K):
+        step(i)
+    torch.cuda.synchronize()
+    prof = N.profile_report()
+    N.profile_enable(False)
+    kern = {k: {"launches": n, "avg_us": 1e3 * t / n, "share": 0.0} for k, (n, t) in prof.items()}
+    lib_ms = sum(t for _, t in prof.values())
+    for k, (n, t) in prof.items():
+        kern[k]["share"] = t / lib_ms if lib_ms else 0.0
+    dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+
+    # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the BEV map ---------------------
+    hf_host = [s[0].cpu().pin_memory() for s in sets]
+    md_host = [{k: (v.cpu().pin_memory() if v is not None else None) for k, v in s[1].items()} for s in sets]
+    bev_host = torch.empty(B, shape.channels, shape.grid[1], shape.grid[0]).pin_memory()
+    h2d = hf_host[0].numel() * 4 + sum(v.numel() * 4 for v in md_host[0].values() if v is not None)
+
+    def e2e_step(i):
+        hf = hf_host[i % nsets].to(dev, non_blocking=True)
+        md = {k: (v.to(dev, non_blocking=True) if v is not None else None) for k, v in md_host[i % nsets].items()}
+        with torch.no_grad():
+            bev = mod.forward_single_sweep(hf, md)
+        bev_host.copy_(bev, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    frames_total = B * K * world
+    value = frames_total / (ms * 1e-3)
+    e2e_value = frames_total / (ms_e2e * 1e-3)
+
+    extra = {}
+    if rank == 0 and not args.quick:
+        extra = extra_measurements(args, shape, mod, sets, dev)
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = _peaks()
+    alg_bytes = shape.fused_forward_bytes() * B           # 8.77 MB/frame at DAIR-R50
+    step_lib_ms = lib_ms / K if K else 0.0
+    achieved = alg_bytes / (step_lib_ms * 1e-3) / 1e9 if step_lib_ms else 0.0
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None,
+        "kernel": "fused lift-splat forward = all library kernels of one step (plan + forward)",
+        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": step_lib_ms, "peak_source": peak_src,
+        "frac_of_8TBs_nominal": achieved / 8000.0,
+        "dominant_kernel": dominant, "dominant_share": kern[dominant]["share"] if dominant else None,
+        "kernels": kern,
+    }
+    cpu = None
+    if world == 1:
+        fps, n, cores, total = cpu_reference_run(shape, 6, 1, budget_s=25.0)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} frame(s) of {shape.name}, forward only, torch-CPU port of the reference path "
+                         f"(oracle/lift_splat_oracle.py), {total:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{shape.name} fused lift-splat forward (softmax + per-frame geometry/plan + BEV "
+                               f"reduction), {B} frames per step per GPU, distinct calibration per frame",
+                   "shape": shape.name, "frames_per_step_per_gpu": B, "D": shape.D, "fH": shape.fH, "fW": shape.fW,
+                   "C": shape.channels, "grid": list(shape.grid), "arith": "PAIR (torch-CUDA bmm order)",
+                   "l2": f"working set per step ({(in_bytes + out_bytes) / 1e6:.0f} MB in+out, 2 rotating input "
+                         f"sets) exceeds the 126 MB L2",
+                   "sharding": "frames across ranks, no collective (replicas only)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    if extra:
+        line["extra"] = extra
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def _time_loop(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extra_measurements(args, shape, mod, sets, dev):
+    """Secondary numbers (not the headline): training step, cached plan, batch-1 latency, the op-level
+    drop-in and the reference's own kernel recompiled for sm_100a on the same inputs."""
+    from sgv3d_b200 import _native as N, voxel_pooling, lift_splat
+    out = {}
+    B = args.batch
+    hf, md, mats = sets[0]
+    D, C = shape.D, shape.channels
+    peak, _ = _peaks()
+    height = hf[:, :D].softmax(1).contiguous()
+    ctx = hf[:, D:].contiguous()
+    plan = mod.make_plan(md, 0, C)
+    gb = torch.randn(B, C, shape.grid[1], shape.grid[0], device=dev)
+    it = max(5, args.steps // 2)
+    ms_plan = _time_loop(plan.rebuild, it)
+    ms_fwd = _time_loop(lambda: plan.forward(height, ctx), it)
+    ms_bwd = _time_loop(lambda: plan.backward(gb, height, ctx), it)
+    fb = shape.fused_forward_bytes() * B
+    bb = shape.fused_backward_bytes() * B
+    out["phases_ms"] = {"plan": ms_plan, "forward_cached_plan": ms_fwd, "backward": ms_bwd}
+    out["cached_plan_forward"] = {"frames_per_s": B / (ms_fwd * 1e-3), "achieved_GBs": fb / ms_fwd / 1e6,
+                                  "frac_of_measured_peak": fb / ms_fwd / 1e6 / peak}
+    out["train_step_fwd_bwd"] = {"frames_per_s": B / ((ms_plan + ms_fwd + ms_bwd) * 1e-3),
+                                 "achieved_GBs": (fb + bb) / (ms_plan + ms_fwd + ms_bwd) / 1e6,
+                                 "frac_of_measured_peak": (fb + bb) / (ms_plan + ms_fwd + ms_bwd) / 1e6 / peak,
+                                 "algorithmic_bytes": fb + bb}
+    # batch-1 latency through the module call site
+    md1 = {k: (v[:1].contiguous() if v is not None else None) for k, v in md.items()}
+    hf1 = hf[:1].contiguous()
+    with torch.no_grad():
+        out["batch1_latency_us"] = 1e3 * _time_loop(lambda: mod.forward_single_sweep(hf1, md1), 20)
+    # op-level drop-in vs the reference kernel (materialised frustum features are an API input there)
+    nb = min(B, 4)
+    idx = mod.get_geometry_indices(md["sensor2ego_mats"][:nb, 0], md["sensor2virtual_mats"][:nb, 0],
+                                   md["intrin_mats"][:nb, 0], md["ida_mats"][:nb, 0],
+                                   md["reference_heights"][:nb, 0], md["bda_mat"][:nb])
+    feat = (height[:nb].unsqueeze(1) * ctx[:nb].unsqueeze(2)).reshape(nb, 1, C, D, shape.fH, shape.fW)
+    feat = feat.permute(0, 1, 3, 4, 5, 2).contiguous()
+    with torch.no_grad():
+        ms_op = _time_loop(lambda: voxel_pooling(idx, feat, list(shape.grid)), 5)
+    ob = shape.op_forward_bytes() * nb
+    out["op_level_forward"] = {"frames": nb, "ms": ms_op, "frames_per_s": nb / (ms_op * 1e-3),
+                               "achieved_GBs": ob / ms_op / 1e6, "frac_of_measured_peak": ob / ms_op / 1e6 / peak}
+    try:
+        from oracle import c_oracle as CO
+        if CO.reference_kernel_available():
+            npts = shape.points_per_frame
+            X, Y, Z = shape.grid
+            o = torch.zeros(nb, Y, X, C, device=dev)
+            pm = torch.full((nb, npts, 3), -1, dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream().cuda_stream
+
+            def ref():
+                o.zero_(); pm.fill_(-1)
+                CO.reference_voxel_pooling_forward(nb, npts, C, X, Y, Z, idx.data_ptr(), feat.data_ptr(),
+                                                   o.data_ptr(), pm.data_ptr(), stream)
+            ms_ref = _time_loop(ref, 5)
+            out["reference_kernel_sm100a_forward"] = {"frames": nb, "ms": ms_ref, "frames_per_s": nb / (ms_ref * 1e-3),
+                                                      "achieved_GBs": ob / ms_ref / 1e6,
+                                                      "note": "reference atomicAdd kernel recompiled unmodified, incl. its output/pos_memo fills"}
+    except Exception as e:  # the oracle is optional for the bench
+        out["reference_kernel_sm100a_forward"] = {"error": str(e)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--shape", default="dair_r50")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,13 @@ SGV3D_API int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, in
  * `gpu_launches`). */
 SGV3D_API int64_t sgv3d_launch_count(int reset);
 
+/* Measurement aid (bench.py's roofline): while enabled, every kernel this library launches on
+ * the calling thread is bracketed by CUDA events on its launch stream.  sgv3d_profile_report()
+ * waits for them, writes one "kernel_name,launches,total_ms" line per kernel into buf, clears
+ * the accumulators and returns the text length.  Off by default; zero cost when off. */
+SGV3D_API int sgv3d_profile_enable(int on);
+SGV3D_API long sgv3d_profile_report(char *buf, size_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ SYMBOLS = (
     "sgv3d_geometry_quantize",
     "sgv3d_lift_splat_workspace_bytes", "sgv3d_lift_splat_plan", "sgv3d_lift_splat_forward",
     "sgv3d_lift_splat_backward", "sgv3d_lift_splat_plan_expand",
+    "sgv3d_profile_enable", "sgv3d_profile_report",
 )
 
 
@@ -74,6 +75,10 @@ def lib() -> ctypes.CDLL:
     L.sgv3d_lift_splat_backward.argtypes = [P] + [c_void_p] * 6 + [c_size_t, c_void_p]
     L.sgv3d_lift_splat_plan_expand.restype = c_int
     L.sgv3d_lift_splat_plan_expand.argtypes = [P] + [c_void_p] * 2 + [c_size_t, c_void_p]
+    L.sgv3d_profile_enable.restype = c_int
+    L.sgv3d_profile_enable.argtypes = [c_int]
+    L.sgv3d_profile_report.restype = ctypes.c_long
+    L.sgv3d_profile_report.argtypes = [ctypes.c_char_p, c_size_t]
     if L.sgv3d_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsgv3d_b200 ABI {L.sgv3d_abi_version()} != expected {ABI_VERSION}")
     _lib = L
@@ -90,6 +95,21 @@ def check(status: int) -> None:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().sgv3d_launch_count(1 if reset else 0))
+
+
+def profile_enable(on: bool) -> None:
+    lib().sgv3d_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total_ms)} since the last report (synchronises the recorded events)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().sgv3d_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(",", 2)
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def ptr(t) -> int:

@@ -19,6 +19,11 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // ---- host-side status plumbing --------------------------------------------------------------
 void set_error(const char *fmt, ...);
 int64_t &launch_counter();
+// optional per-kernel CUDA-event timing (sgv3d_profile_enable / sgv3d_profile_report):
+// prof_begin() marks the start of an API call on its stream, prof_mark() is recorded right after
+// every launch; a kernel's time is the span between its mark and the previous one.
+void prof_begin(cudaStream_t stream);
+void prof_mark(const char *name);
 
 #define SGV3D_REQUIRE(cond, ...)            \
   do {                                      \
@@ -32,6 +37,7 @@ int64_t &launch_counter();
 #define SGV3D_CHECK_LAUNCH(name)                                                      \
   do {                                                                                \
     ++::sgv3d::launch_counter();                                                      \
+    ::sgv3d::prof_mark(name);                                                         \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess) {                                                         \
       ::sgv3d::set_error("kernel %s failed to launch: %s", name, cudaGetErrorString(e__)); \

@@ -69,6 +69,7 @@ extern "C" int sgv3d_geometry_quantize(int arith, int B, int Nc, int D, int fH, 
   dim3 g(ceil_div(fH * fW, kThreads), B * Nc);
   const size_t smem = sizeof(float) * D;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
   if (arith == SGV3D_ARITH_PAIR)
     geometry_quantize_kernel<SGV3D_ARITH_PAIR><<<g, kThreads, smem, s>>>(
         Nc, D, fH, fW, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda, ref_heights, grid, idx_out, xyz_out);

@@ -580,6 +580,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
   geom::Grid grid;
   for (int k = 0; k < 3; ++k) { grid.lower[k] = lower3[k]; grid.size[k] = size3[k]; }
   grid.X = m.X; grid.Y = m.Y; grid.Z = m.Z;
@@ -633,6 +634,7 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
   if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
   dim3 gc(m.nchunks, m.B);
   ls_weights_kernel<true><<<gc, kChunk, 0, s>>>(m, height, w.run_cnt, w.run_d, w.run_dst, w.w_vm);
@@ -653,6 +655,7 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_backward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
   const int gpad = ceil_div(m.C, 4) * 4;
   if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
   launch_transpose_pad<float, float>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
@@ -683,6 +686,7 @@ extern "C" int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, i
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan_expand")) return rc;
   dim3 gc(m.nchunks, m.B);
+  prof_begin(static_cast<cudaStream_t>(stream));
   ls_expand_kernel<true><<<gc, kChunk, 0, static_cast<cudaStream_t>(stream)>>>(
       m, w.run_cnt, w.run_d, w.run_vox, nullptr, nullptr, vox_out);
   SGV3D_CHECK_LAUNCH("ls_expand_kernel(vox)");

@@ -221,6 +221,7 @@ extern "C" int sgv3d_voxel_pooling_forward(int B, int N, int C, int X, int Y, in
   SGV3D_REQUIRE(C <= 1024, "voxel_pooling_forward: C=%d > 1024 unsupported", C);
   SGV3D_REQUIRE(out != nullptr, "voxel_pooling_forward: out is null");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
   if (B == 0) return SGV3D_OK;
   const int V = X * Y;
   if (N == 0) {
@@ -294,6 +295,7 @@ extern "C" int sgv3d_voxel_pooling_backward(int B, int N, int C, int X, int Y, c
   if (B == 0 || N == 0) return SGV3D_OK;
   SGV3D_REQUIRE(grad_out && pos_memo && grad_features, "voxel_pooling_backward: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
   const float *g_cl = grad_out;
   long long lsb = sb, lsy = sy, lsx = sx;
   if (sc != 1) {

