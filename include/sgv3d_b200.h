@@ -122,7 +122,8 @@ SGV3D_API int sgv3d_geometry_quantize(int arith, int B, int Nc, int D, int fH, i
  * (3) fused lift-splat.  The plan (index) depends only on calibration + grid; forward/backward
  *     (values) depend on the activations.  Static roadside cameras can build the plan once.
  *
- *     height   fp32 [B*Nc, D, fH, fW]   softmax-ed height-bin probabilities (lss_fpn.py:462)
+ *     height   fp32 [B*Nc, D, fH, fW]   softmax-ed height-bin probabilities (lss_fpn.py:462), or the
+ *                                       raw logits when desc.height_is_logits = 1
  *     context  fp32|bf16 [B*Nc, C, fH, fW]
  *     bev      fp32 [B, C, Y, X]        contiguous, fully written (lss_fpn.py:494-495)
  *     BEV[b,c,y,x] = sum over kept points (n,d,h,w)->(x,y) of height[bn,d,h,w]*context[bn,c,h,w]
@@ -132,7 +133,14 @@ typedef struct sgv3d_lift_splat_desc {
   int32_t X, Y, Z;             /* voxel grid (voxel_num) */
   int32_t arith;               /* SGV3D_ARITH_* */
   int32_t ctx_dtype;           /* SGV3D_DTYPE_* */
-  int32_t reserved[5];
+  int32_t height_is_logits;    /* 1: `height` holds raw height-net logits; the softmax over D
+                                  (lss_fpn.py:462) and its backward run inside the kernels */
+  /* Element strides between consecutive cameras (0 => densely packed).  They let `height` and
+   * `context` (and their gradients) be views into the height net's (B*Nc, D + C, fH, fW) output,
+   * lss_fpn.py:461-466, without a copy.  Within one camera the [D|C][fH][fW] block is dense. */
+  int64_t height_batch_stride, ctx_batch_stride;
+  int64_t grad_height_batch_stride, grad_ctx_batch_stride;
+  int32_t reserved[4];
 } sgv3d_lift_splat_desc;
 
 SGV3D_API size_t sgv3d_lift_splat_workspace_bytes(const sgv3d_lift_splat_desc *desc);

@@ -30,8 +30,11 @@ SYMBOLS = (
 
 class LiftSplatDesc(ctypes.Structure):
     """``struct sgv3d_lift_splat_desc`` (include/sgv3d_b200.h)."""
-    _fields_ = [(n, c_int32) for n in ("B", "Nc", "D", "fH", "fW", "C", "X", "Y", "Z", "arith", "ctx_dtype")]
-    _fields_.append(("reserved", c_int32 * 5))
+    _fields_ = ([(n, c_int32) for n in ("B", "Nc", "D", "fH", "fW", "C", "X", "Y", "Z", "arith", "ctx_dtype",
+                                        "height_is_logits")]
+                + [(n, c_int64) for n in ("height_batch_stride", "ctx_batch_stride",
+                                          "grad_height_batch_stride", "grad_ctx_batch_stride")]
+                + [("reserved", c_int32 * 4)])
 
 
 _lib = None

@@ -12,6 +12,8 @@
 // its inputs are bitwise unchanged (always, for the reference's z-preserving IDA matrices).
 #pragma once
 
+#include <string.h>
+
 #include "common.cuh"
 
 namespace sgv3d {
@@ -25,12 +27,18 @@ struct Camera {
   float Bd[16];  // bda_mat (only read when has_bda)          lss_fpn.py:394-398
   float ref_h;   // reference_heights[b, n]                   lss_fpn.py:352-354
   int has_bda;
+  int bda_fast;  // bda is bitwise the identity and row 3 of Me is small: bda @ p == p for finite p
 };
 
 struct Grid {
   float lower[3];  // fp32(voxel_coord - voxel_size / 2.0)
   float size[3];   // voxel_size
   int X, Y, Z;
+  // Exact z-range test without a division: for t = fp32(g.z - lower.z),
+  //   0 <= trunc(RN(t / size.z)) < Z   <=>   !(t <= zt_lo) && !(t >= zt_hi)
+  // zt_lo / zt_hi are found on the host by bisection over float bit patterns with the same IEEE
+  // division (RN(t/s) is monotone in t).  NaN passes both tests, as cvt.rzi(NaN) = 0 is in range.
+  float zt_lo, zt_hi;
 };
 
 template <int ARITH>
@@ -123,6 +131,52 @@ struct PixelRay {
       gx = bx; gy = by; gz = bz;
     }
   }
+
+  // Voxel id (y*X + x, or -1 if dropped) of the point at height bin value z: point() + quantise +
+  // range test (lss_fpn.py:487-488, voxel_pooling_forward_cuda.cu:24) with two exact shortcuts that
+  // only the index path may take: the z test by thresholds, and skipping an identity bda.
+  __device__ __forceinline__ int voxel(const Camera &cam, const Grid &g, float z) {
+    const float p0x = dot2_tail<ARITH>(head[0], cam.A + 0, z, 1.0f);
+    const float p0y = dot2_tail<ARITH>(head[1], cam.A + 4, z, 1.0f);
+    const float p0z = dot2_tail<ARITH>(head[2], cam.A + 8, z, 1.0f);
+    const float p0w = dot2_tail<ARITH>(head[3], cam.A + 12, z, 1.0f);
+    const float hgt = __fadd_rn(__fmul_rn(-1.0f, p0z), cam.ref_h);
+    const float n0 = __fmul_rn(p0x, 10.0f), n1 = __fmul_rn(p0y, 10.0f), n3 = p0w;
+    if (!have_pv || __float_as_uint(n0) != __float_as_uint(q0) ||
+        __float_as_uint(n1) != __float_as_uint(q1) || __float_as_uint(n3) != __float_as_uint(q3)) {
+      q0 = n0; q1 = n1; q3 = n3;
+      pv0 = dot4<ARITH>(cam.Mv + 0, n0, n1, 10.0f, n3);
+      pv1 = dot4<ARITH>(cam.Mv + 4, n0, n1, 10.0f, n3);
+      pv2 = dot4<ARITH>(cam.Mv + 8, n0, n1, 10.0f, n3);
+      have_pv = true;
+    }
+    const float ratio = __fdiv_rn(hgt, pv1);
+    const float e0 = __fmul_rn(pv0, ratio), e1 = __fmul_rn(pv1, ratio), e2 = __fmul_rn(pv2, ratio);
+    float gx = dot4<ARITH>(cam.Me + 0, e0, e1, e2, 1.0f);
+    float gy = dot4<ARITH>(cam.Me + 4, e0, e1, e2, 1.0f);
+    float gz = dot4<ARITH>(cam.Me + 8, e0, e1, e2, 1.0f);
+    if (cam.has_bda) {
+      // identity bda: 1*x + 0*y + 0*z + 0*w == x (up to the sign of a zero, which cannot change an
+      // index) as long as every operand is finite and w cannot overflow; otherwise evaluate it.
+      const float big = 1e15f;
+      const bool tame = fabsf(e0) < big && fabsf(e1) < big && fabsf(e2) < big && fabsf(gx) < big &&
+                        fabsf(gy) < big && fabsf(gz) < big;
+      if (!(cam.bda_fast && tame)) {
+        const float gw = dot4<ARITH>(cam.Me + 12, e0, e1, e2, 1.0f);
+        const float bx = dot4<ARITH>(cam.Bd + 0, gx, gy, gz, gw);
+        const float by = dot4<ARITH>(cam.Bd + 4, gx, gy, gz, gw);
+        const float bz = dot4<ARITH>(cam.Bd + 8, gx, gy, gz, gw);
+        gx = bx; gy = by; gz = bz;
+      }
+    }
+    const float tz = __fsub_rn(gz, g.lower[2]);
+    if (tz <= g.zt_lo || tz >= g.zt_hi) return -1;
+    const int ix = __float2int_rz(__fdiv_rn(__fsub_rn(gx, g.lower[0]), g.size[0]));
+    if ((unsigned)ix >= (unsigned)g.X) return -1;
+    const int iy = __float2int_rz(__fdiv_rn(__fsub_rn(gy, g.lower[1]), g.size[1]));
+    if ((unsigned)iy >= (unsigned)g.Y) return -1;
+    return iy * g.X + ix;
+  }
 };
 
 // :487-488  ((g - lower) / size).int() -- fp32 subtract, IEEE divide, cvt.rzi.s32.f32
@@ -152,7 +206,47 @@ __device__ __forceinline__ void load_camera(Camera *s, const float *ida_inv, con
   if (t == 0) {
     s->ref_h = ref_h[bn];
     s->has_bda = bda != nullptr;
+    int fast = bda != nullptr;
+    if (bda) {
+      for (int k = 0; k < 16; ++k) {
+        const float want = (k % 5 == 0) ? 1.0f : 0.0f;
+        fast = fast && (__float_as_uint(bda[16 * (size_t)b + k]) == __float_as_uint(want));
+      }
+      for (int k = 12; k < 16; ++k) fast = fast && (fabsf(me[16 * (size_t)bn + k]) < 1e15f);
+    }
+    s->bda_fast = fast;
   }
+}
+
+// ---- host: exact thresholds for the z-range test ------------------------------------------------
+inline int host_quantize1(float t, float size) {
+  const float q = t / size;  // IEEE single division on the host as well (no fast-math)
+  if (q != q) return 0;
+  if (q >= 2147483648.0f) return 2147483647;
+  if (q <= -2147483648.0f) return (int)0x80000000;
+  return (int)q;
+}
+inline float ordered_to_float(long long k) {  // monotone bijection int <-> float (finite range)
+  const unsigned int u = k >= 0 ? (unsigned int)k : 0x80000000u | (unsigned int)(-k);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// largest t with trunc(t/size) <= -1  and  smallest t with trunc(t/size) >= Z  (size > 0)
+inline void z_thresholds(float size, int Z, float *lo, float *hi) {
+  const long long kmax = 0x7f7fffff;  // FLT_MAX
+  long long a = -kmax, b = kmax;       // hi: first k in [a,b] with quantize >= Z
+  while (a < b) {
+    const long long m = a + (b - a) / 2;
+    if (host_quantize1(ordered_to_float(m), size) >= Z) b = m; else a = m + 1;
+  }
+  *hi = ordered_to_float(a);
+  a = -kmax; b = kmax;                 // lo: last k with quantize <= -1
+  while (a < b) {
+    const long long m = a + (b - a + 1) / 2;
+    if (host_quantize1(ordered_to_float(m), size) <= -1) a = m; else b = m - 1;
+  }
+  *lo = ordered_to_float(a);
 }
 
 }  // namespace geom

@@ -14,14 +14,16 @@
 //     row_ptr_kernel          CSR offsets per voxel + inverse permutation (run -> sorted slot)
 //   FORWARD (values)
 //     transpose_pad_kernel    context NCHW -> one 16B-aligned row per pixel
-//     ls_weights_kernel       w[run] = sum_{d in run} height[d,pixel]   (coalesced, lockstep in d)
-//     ls_reduce_kernel        per voxel: sum_j w[j] * ctx_row[pixel_j] in sorted (deterministic)
-//                             order, staged through smem, written NCHW-coalesced incl. zero rows
+//     ls_weights_kernel       [softmax over D fused] w[run] = sum_{d in run} p[d,pixel]; the height
+//                             columns of 128 pixels are staged in smem with cp.async (all loads in flight)
+//     ls_reduce_kernel        per 32-voxel strip: entries staged in smem, per voxel
+//                             sum_j w[j] * ctx_row[pixel_j] in sorted (deterministic) order,
+//                             written NCHW-coalesced incl. zero rows
 //   BACKWARD (values; pixel-major, no sort needed)
 //     transpose_pad_kernel    grad_bev NCHW -> one row per voxel
 //     ls_weights_kernel       w per run (pixel-major destination)
 //     ls_backward_gather_kernel  warp/pixel: g_ctx_row = sum_r w_r*G[voxel_r]; gw_r = <ctx_row, G[voxel_r]>
-//     ls_expand_gheight_kernel   g_height[d,pixel] = gw[run(d)] (0 for dropped bins), coalesced
+//     ls_expand_kernel        g_height[d,pixel] = gw[run(d)] (0 for dropped bins) [softmax backward fused]
 //     transpose_pad_kernel    g_ctx rows -> NCHW
 //
 // No floating-point atomics anywhere; every sum has a fixed order => bitwise reproducible.
@@ -45,6 +47,9 @@ struct Dims {
   int Cpad;     // padded row length of the channels-last copies (elements)
   int cap;      // max runs per frame (= ELL slots per frame)
   int bins2, nblk2;
+  int logits;             // height tensor holds raw logits (softmax over D fused)
+  long long hs, cs;       // element strides between consecutive cameras of height / context
+  long long ghs, gcs;     // same for grad_height / grad_context
 };
 
 struct Workspace {
@@ -68,6 +73,11 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   m.cap = m.nchunks * kChunk * m.D;
   m.bins2 = (m.V >> sort::kLowBits) + 1;
   m.nblk2 = ceil_div(m.cap, sort::kItemsPerBlock);
+  m.logits = d->height_is_logits;
+  m.hs = d->height_batch_stride ? d->height_batch_stride : (long long)m.D * m.P;
+  m.cs = d->ctx_batch_stride ? d->ctx_batch_stride : (long long)m.C * m.P;
+  m.ghs = d->grad_height_batch_stride ? d->grad_height_batch_stride : (long long)m.D * m.P;
+  m.gcs = d->grad_ctx_batch_stride ? d->grad_ctx_batch_stride : (long long)m.C * m.P;
   return m;
 }
 
@@ -106,6 +116,7 @@ __device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t)
 
 // ---------------------------------------------------------------------------------------------
 // PLAN 1/3: geometry -> voxel id per height bin -> runs.  grid (nchunks, B), 128 threads.
+// Pure ALU work (no global reads besides three tiny tables); two bins per iteration for ILP.
 // ---------------------------------------------------------------------------------------------
 template <int ARITH>
 __global__ void __launch_bounds__(kChunk)
@@ -134,15 +145,7 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
     geom::PixelRay<ARITH> ray;
     ray.init(cam, u_tab[w], v_tab[h]);
     int cur = -1, d0 = 0;
-    for (int d = 0; d <= m.D; ++d) {
-      int vox = -2;  // sentinel closing the last run
-      if (d < m.D) {
-        float gx, gy, gz;
-        ray.point(cam, z_s[d], gx, gy, gz);
-        vox = geom::voxel_of(grid, geom::quantize1(gx, grid.lower[0], grid.size[0]),
-                             geom::quantize1(gy, grid.lower[1], grid.size[1]),
-                             geom::quantize1(gz, grid.lower[2], grid.size[2]));
-      }
+    auto step = [&](int d, int vox) {
       if (vox != cur) {
         if (cur >= 0) {
           const size_t s = ell_slot(frame_chunk, m.D, r, t);
@@ -154,7 +157,19 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
         cur = vox;
         d0 = d;
       }
+    };
+    int d = 0;
+    for (; d + 2 <= m.D; d += 2) {
+      const int v0 = ray.voxel(cam, grid, z_s[d]);
+      const int v1 = ray.voxel(cam, grid, z_s[d + 1]);
+      step(d, v0);
+      step(d + 1, v1);
     }
+    if (d < m.D) {
+      step(d, ray.voxel(cam, grid, z_s[d]));
+      ++d;
+    }
+    step(m.D, -2);  // sentinel closes the last run
   }
   run_cnt[(size_t)frame_chunk * kChunk + t] = r;
   __syncthreads();
@@ -218,42 +233,94 @@ struct PlanFinalize {
 };
 
 // ---------------------------------------------------------------------------------------------
-// FORWARD / BACKWARD: run weights  w = sum_{d in run} height[d, pixel].
-// Thread per pixel, all lanes walk d in lockstep so every height row is read fully coalesced,
-// exactly once.  DST_SORTED: write to the run's voxel-major slot (forward) else pixel-major ELL.
+// Column staging: the D x 128 block of height values (or logits) of one pixel chunk goes to shared
+// memory with cp.async -- every load of the CTA is in flight at once, rows are read coalesced and
+// exactly once.  col[d * kChunk + t].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+__device__ __forceinline__ void stage_columns(float *col, const float *__restrict__ src /*camera base*/,
+                                              int D, int P, int p0, bool vec16) {
+  const int t = threadIdx.x;
+  const int npx = min(kChunk, P - p0);
+  if (vec16 && npx == kChunk) {
+    // one warp copies one 512-byte row per instruction
+    const int lane = t & 31, wid = t >> 5;
+    for (int d = wid; d < D; d += kChunk / 32)
+      cp_async_16(col + d * kChunk + lane * 4, src + (size_t)d * P + p0 + lane * 4);
+  } else if (t < npx) {
+    for (int d = 0; d < D; ++d) cp_async_4(col + d * kChunk + t, src + (size_t)d * P + p0 + t);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+}
+
+// In-place softmax over D of this thread's staged column (matches torch.softmax within fp32
+// rounding: exp(x - max) / sum).  col holds probabilities afterwards.
+__device__ __forceinline__ void softmax_column(float *col, int D, int t) {
+  float mx = -INFINITY;
+  for (int d = 0; d < D; ++d) mx = fmaxf(mx, col[d * kChunk + t]);
+  float sum = 0.0f;
+  for (int d = 0; d < D; ++d) {
+    const float e = expf(__fsub_rn(col[d * kChunk + t], mx));
+    col[d * kChunk + t] = e;
+    sum = __fadd_rn(sum, e);
+  }
+  const float inv = __fdiv_rn(1.0f, sum);
+  for (int d = 0; d < D; ++d) col[d * kChunk + t] = __fmul_rn(col[d * kChunk + t], inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FORWARD / BACKWARD: run weights  w = sum_{d in run} p[d, pixel]  (ascending d, fixed order).
+// DST_SORTED: write to the run's voxel-major slot (forward) else pixel-major ELL (backward).
 // ---------------------------------------------------------------------------------------------
 template <bool DST_SORTED>
 __global__ void __launch_bounds__(kChunk)
-ls_weights_kernel(Dims m, const float *__restrict__ height, const int *__restrict__ run_cnt,
-                  const int *__restrict__ run_d, const int *__restrict__ run_dst,
-                  float *__restrict__ w_out) {
+ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
+                  const int *__restrict__ run_cnt, const int *__restrict__ run_d,
+                  const int *__restrict__ run_dst, float *__restrict__ w_out) {
+  extern __shared__ float col[];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;
   const int t = threadIdx.x;
-  const int p = ci * kChunk + t;
-  if (p >= m.P) return;
+  const int p0 = ci * kChunk;
+  stage_columns(col, height + (size_t)(b * m.Nc + n) * m.hs, m.D, m.P, p0, vec16 != 0);
+  if (p0 + t >= m.P) return;
   const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
   if (cnt == 0) return;
-  const float *hp = height + (size_t)(b * m.Nc + n) * m.D * m.P + p;
-  int r = 0;
-  size_t s = ell_slot(frame_chunk, m.D, 0, t);
-  int packed = run_d[s];
-  int d0 = packed & 0xffff, d1 = packed >> 16;
-  float acc = 0.0f;
-  // every lane starts at d = 0 so that the warp reads each height row as one coalesced request
-  for (int d = 0; d < m.D; ++d) {
-    const float hv = ldg_stream_f1(hp + (size_t)d * m.P);
-    if (d >= d0) acc = __fadd_rn(acc, hv);
-    if (d + 1 == d1) {
-      const size_t o = DST_SORTED ? (size_t)b * m.cap + run_dst[s] : s;
-      w_out[o] = acc;
-      acc = 0.0f;
-      if (++r == cnt) break;
-      s = ell_slot(frame_chunk, m.D, r, t);
-      packed = run_d[s];
-      d0 = packed & 0xffff;
-      d1 = packed >> 16;
+  if (m.logits) softmax_column(col, m.D, t);
+  // batch the (strided) run descriptors 4 at a time
+  for (int r0 = 0; r0 < cnt; r0 += 4) {
+    int packed[4], dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      packed[u] = 0; dst[u] = 0;
+      if (r0 + u < cnt) {
+        const size_t s = ell_slot(frame_chunk, m.D, r0 + u, t);
+        packed[u] = run_d[s];
+        if (DST_SORTED) dst[u] = run_dst[s];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u < cnt) {
+        const int d0 = packed[u] & 0xffff, d1 = packed[u] >> 16;
+        float acc = 0.0f;
+        for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
+        const size_t o = DST_SORTED ? (size_t)b * m.cap + dst[u] : ell_slot(frame_chunk, m.D, r0 + u, t);
+        w_out[o] = acc;
+      }
     }
   }
 }
@@ -261,7 +328,9 @@ ls_weights_kernel(Dims m, const float *__restrict__ height, const int *__restric
 // ---------------------------------------------------------------------------------------------
 // FORWARD: per-voxel weighted gather of context rows.
 // grid (ceil(V/32), B), 256 threads.  CTA = 32 consecutive voxels (one 128-byte strip of every
-// output channel plane); warp w owns voxels 4w..4w+3; lanes own 4-channel slices of a row.
+// output channel plane).  The strip's CSR offsets and its (pixel, weight) entries are staged in
+// shared memory first (coalesced, one round trip), then warp w accumulates voxels 4w..4w+3 with
+// 8 independent 128-bit row loads in flight; lanes own 4-channel slices of a row.
 // ---------------------------------------------------------------------------------------------
 template <typename CT>
 struct RowLoad;
@@ -282,6 +351,8 @@ struct RowLoad<__nv_bfloat16> {
 };
 
 constexpr int kTileV = 32;
+constexpr int kStage = 1024;  // entries staged per round (8 KB)
+constexpr int kRowsInFlight = 8;
 
 template <typename CT, int NCH>
 __global__ void __launch_bounds__(256)
@@ -289,95 +360,101 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
                  const int *__restrict__ vm_pix, const float *__restrict__ w_vm,
                  float *__restrict__ bev) {
   extern __shared__ float tile[];  // [C][kTileV + 1]
+  __shared__ int s_rp[kTileV + 1];
+  __shared__ int s_pix[kStage];
+  __shared__ float s_w[kStage];
   const int b = blockIdx.y;
   const int v0 = blockIdx.x * kTileV;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int *rp = row_ptr + (size_t)b * (m.V + 1);
   const int vend = min(v0 + kTileV, m.V);
+  const int nv = vend - v0;
   float *out = bev + (size_t)b * m.C * m.V;
-  const int tile_lo = rp[v0], tile_hi = rp[vend];
+  if (tid <= kTileV) s_rp[tid] = rp[min(v0 + tid, vend)];
+  __syncthreads();
+  const int tile_lo = s_rp[0], tile_hi = s_rp[nv];
   if (tile_lo == tile_hi) {  // empty strip: zero rows only
     for (int c = wid; c < m.C; c += 8)
-      if (v0 + lane < vend) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, 0.0f);
+      if (lane < nv) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, 0.0f);
     return;
   }
   const int nslices = m.Cpad / 4;
   const CT *rows = ctxT + (size_t)b * m.Nc * m.P * m.Cpad;
   const int *pix = vm_pix + (size_t)b * m.cap;
   const float *wv = w_vm + (size_t)b * m.cap;
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
-    const int vl = wid * 4 + i;
-    const int v = v0 + vl;
-    float acc[NCH][4];
+
+  float acc[4][NCH][4];  // the warp's 4 voxels
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
-    if (v < vend) {
-      const int lo = rp[v], hi = rp[v + 1];
-      for (int j0 = lo; j0 < hi; j0 += 32) {
-        const int cnt = min(32, hi - j0);
-        int my_pix = 0;
-        float my_w = 0.0f;
-        if (lane < cnt) {
-          my_pix = pix[j0 + lane];
-          my_w = wv[j0 + lane];
-        }
-        int q = 0;
-        for (; q + 4 <= cnt; q += 4) {  // 4 independent row loads in flight
-          float r[4][NCH][4];
-          float ww[4];
+      for (int e = 0; e < 4; ++e) acc[i][k][e] = 0.0f;
+
+  for (int base = tile_lo; base < tile_hi; base += kStage) {
+    const int stage_hi = min(base + kStage, tile_hi);
+    if (base != tile_lo) __syncthreads();
+    for (int j = base + tid; j < stage_hi; j += 256) {
+      s_pix[j - base] = pix[j];
+      s_w[j - base] = wv[j];
+    }
+    __syncthreads();
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const CT *row = rows + (size_t)__shfl_sync(0xffffffffu, my_pix, q + u) * m.Cpad;
-            ww[u] = __shfl_sync(0xffffffffu, my_w, q + u);
+    for (int i = 0; i < 4; ++i) {
+      const int vl = wid * 4 + i;
+      if (vl < nv) {  // warp-uniform
+        const int lo = max(s_rp[vl], base), hi = min(s_rp[vl + 1], stage_hi);
+        for (int q = lo; q < hi; q += kRowsInFlight) {
+          float r[kRowsInFlight][NCH][4];
+          float ww[kRowsInFlight];
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              const int sl = k * 32 + lane;
-              if (sl < nslices) RowLoad<CT>::load(row, sl, r[u][k]);
-              else { r[u][k][0] = r[u][k][1] = r[u][k][2] = r[u][k][3] = 0.0f; }
+          for (int u = 0; u < kRowsInFlight; ++u) {
+            if (q + u < hi) {  // warp-uniform predicate: no dummy arithmetic on padding entries
+              const CT *row = rows + (size_t)s_pix[q + u - base] * m.Cpad;
+              ww[u] = s_w[q + u - base];
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                const int sl = k * 32 + lane;
+                if (sl < nslices) RowLoad<CT>::load(row, sl, r[u][k]);
+              }
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < kRowsInFlight; ++u) {
+            if (q + u < hi) {
 #pragma unroll
-            for (int k = 0; k < NCH; ++k)
+              for (int k = 0; k < NCH; ++k) {
+                if (k * 32 + lane < nslices) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(ww[u], r[u][k][e], acc[k][e]);
-        }
-        for (; q < cnt; ++q) {
-          const CT *row = rows + (size_t)__shfl_sync(0xffffffffu, my_pix, q) * m.Cpad;
-          const float w1 = __shfl_sync(0xffffffffu, my_w, q);
-#pragma unroll
-          for (int k = 0; k < NCH; ++k) {
-            const int sl = k * 32 + lane;
-            if (sl < nslices) {
-              float r1[4];
-              RowLoad<CT>::load(row, sl, r1);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(w1, r1[e], acc[k][e]);
+                  for (int e = 0; e < 4; ++e) acc[i][k][e] = __fmaf_rn(ww[u], r[u][k][e], acc[i][k][e]);
+                }
+              }
             }
           }
         }
       }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vl = wid * 4 + i;
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = (k * 32 + lane) * 4 + e;
-        if (c < m.C) tile[c * (kTileV + 1) + vl] = acc[k][e];
+        if (c < m.C) tile[c * (kTileV + 1) + vl] = acc[i][k][e];
       }
   }
   __syncthreads();
   for (int c = wid; c < m.C; c += 8)
-    if (v0 + lane < vend) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, tile[c * (kTileV + 1) + lane]);
+    if (lane < nv) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, tile[c * (kTileV + 1) + lane]);
 }
 
 // ---------------------------------------------------------------------------------------------
 // BACKWARD: one warp per pixel.  Lanes hold 4-channel slices of the pixel's context row;
 // for every run: G row gather (128-bit), g_ctx += w*G, gw = <ctx, G> (fixed butterfly order).
+// Four runs are processed together so that four row loads and four butterflies overlap.
 // ---------------------------------------------------------------------------------------------
 template <typename CT, int NCH>
 __global__ void __launch_bounds__(256)
@@ -414,28 +491,47 @@ ls_backward_gather_kernel(Dims m, int gpad, const CT *__restrict__ ctxT, const f
       my_w = w_pm[s];
     }
     float my_gw = 0.0f;
-    for (int q = 0; q < nr; ++q) {
-      const float *grow = gb + (size_t)__shfl_sync(0xffffffffu, my_vox, q) * gpad;
-      const float w1 = __shfl_sync(0xffffffffu, my_w, q);
-      float dot = 0.0f;
+    for (int q = 0; q < nr; q += 4) {
+      float4 g[4][NCH];
+      float w4[4], dot[4];
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        const int sl = k * 32 + lane;
-        if (sl < nslices_g) {
-          const float4 g = __ldg(reinterpret_cast<const float4 *>(grow) + sl);
-          acc[k][0] = __fmaf_rn(w1, g.x, acc[k][0]);
-          acc[k][1] = __fmaf_rn(w1, g.y, acc[k][1]);
-          acc[k][2] = __fmaf_rn(w1, g.z, acc[k][2]);
-          acc[k][3] = __fmaf_rn(w1, g.w, acc[k][3]);
-          dot = __fmaf_rn(cx[k][0], g.x, dot);
-          dot = __fmaf_rn(cx[k][1], g.y, dot);
-          dot = __fmaf_rn(cx[k][2], g.z, dot);
-          dot = __fmaf_rn(cx[k][3], g.w, dot);
+      for (int u = 0; u < 4; ++u) {
+        const int src = min(q + u, nr - 1);
+        const float *grow = gb + (size_t)__shfl_sync(0xffffffffu, my_vox, src) * gpad;
+        w4[u] = __shfl_sync(0xffffffffu, my_w, src);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int sl = k * 32 + lane;
+          g[u][k] = (sl < nslices_g && q + u < nr) ? __ldg(reinterpret_cast<const float4 *>(grow) + sl)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, o));
-      if (lane == q) my_gw = dot;
+      for (int u = 0; u < 4; ++u) {
+        dot[u] = 0.0f;
+        if (q + u < nr) {
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            if (k * 32 + lane < nslices_g) {
+              acc[k][0] = __fmaf_rn(w4[u], g[u][k].x, acc[k][0]);
+              acc[k][1] = __fmaf_rn(w4[u], g[u][k].y, acc[k][1]);
+              acc[k][2] = __fmaf_rn(w4[u], g[u][k].z, acc[k][2]);
+              acc[k][3] = __fmaf_rn(w4[u], g[u][k].w, acc[k][3]);
+              dot[u] = __fmaf_rn(cx[k][0], g[u][k].x, dot[u]);
+              dot[u] = __fmaf_rn(cx[k][1], g[u][k].y, dot[u]);
+              dot[u] = __fmaf_rn(cx[k][2], g[u][k].z, dot[u]);
+              dot[u] = __fmaf_rn(cx[k][3], g[u][k].w, dot[u]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dot[u] = __fadd_rn(dot[u], __shfl_xor_sync(0xffffffffu, dot[u], o));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane == q + u) my_gw = dot[u];
     }
     if (lane < nr) gw_pm[ell_slot(frame_chunk, m.D, r0 + lane, t)] = my_gw;
   }
@@ -448,21 +544,36 @@ ls_backward_gather_kernel(Dims m, int gpad, const CT *__restrict__ ctxT, const f
   }
 }
 
-// g_height[d, pixel] = gw[run containing d], 0 for dropped bins.  Thread per pixel, lockstep in d.
-// EXPAND_VOX: write the voxel id instead (plan_expand debug entry point).
-template <bool EXPAND_VOX>
+// ---------------------------------------------------------------------------------------------
+// g_height[d, pixel] = gw[run containing d], 0 for dropped bins; thread per pixel, coalesced rows.
+// MODE 0: plain.  MODE 1: softmax backward fused (height holds logits):
+//   g_logit[d] = p[d] * (g_p[d] - sum_d' p[d'] g_p[d'])   with  sum_d' p g_p = sum_runs w_run * gw_run.
+// MODE 2: write the voxel id instead (plan_expand debug entry point).
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(kChunk)
-ls_expand_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_d,
-                 const int *__restrict__ run_vox, const float *__restrict__ gw_pm,
+ls_expand_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
+                 const int *__restrict__ run_d, const int *__restrict__ run_vox,
+                 const float *__restrict__ w_pm, const float *__restrict__ gw_pm,
                  float *__restrict__ g_height, int *__restrict__ vox_out) {
+  extern __shared__ float col[];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;
   const int t = threadIdx.x;
-  const int p = ci * kChunk + t;
+  const int p0 = ci * kChunk, p = p0 + t;
+  if (MODE == 1) stage_columns(col, height + (size_t)(b * m.Nc + n) * m.hs, m.D, m.P, p0, vec16 != 0);
   if (p >= m.P) return;
   const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
-  const size_t base = (size_t)(b * m.Nc + n) * m.D * m.P + p;
+  float S = 0.0f;
+  if (MODE == 1) {
+    softmax_column(col, m.D, t);
+    for (int r = 0; r < cnt; ++r) {
+      const size_t s = ell_slot(frame_chunk, m.D, r, t);
+      S = __fmaf_rn(w_pm[s], gw_pm[s], S);
+    }
+  }
+  const size_t base = (MODE == 2 ? (size_t)(b * m.Nc + n) * m.D * m.P : (size_t)(b * m.Nc + n) * m.ghs) + p;
   int r = 0, d0 = m.D, d1 = m.D;
   float gv = 0.0f;
   int vv = -1;
@@ -470,18 +581,21 @@ ls_expand_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict_
     const size_t s = ell_slot(frame_chunk, m.D, 0, t);
     const int packed = run_d[s];
     d0 = packed & 0xffff; d1 = packed >> 16;
-    if (EXPAND_VOX) vv = run_vox[s]; else gv = gw_pm[s];
+    if (MODE == 2) vv = run_vox[s]; else gv = gw_pm[s];
   }
   for (int d = 0; d < m.D; ++d) {
     const bool in = d >= d0 && d < d1;
-    if (EXPAND_VOX) vox_out[base + (size_t)d * m.P] = in ? vv : -1;
+    if (MODE == 2) vox_out[base + (size_t)d * m.P] = in ? vv : -1;
+    else if (MODE == 1)
+      stg_stream_f1(g_height + base + (size_t)d * m.P,
+                    __fmul_rn(col[d * kChunk + t], __fsub_rn(in ? gv : 0.0f, S)));
     else stg_stream_f1(g_height + base + (size_t)d * m.P, in ? gv : 0.0f);
     if (d + 1 == d1) {
       if (++r < cnt) {
         const size_t s = ell_slot(frame_chunk, m.D, r, t);
         const int packed = run_d[s];
         d0 = packed & 0xffff; d1 = packed >> 16;
-        if (EXPAND_VOX) vv = run_vox[s]; else gv = gw_pm[s];
+        if (MODE == 2) vv = run_vox[s]; else gv = gw_pm[s];
       } else {
         d0 = d1 = m.D + 1;
       }
@@ -494,12 +608,15 @@ int validate(const sgv3d_lift_splat_desc *d, const char *who) {
   SGV3D_REQUIRE(d->B >= 0 && d->Nc > 0 && d->D > 0 && d->fH > 0 && d->fW > 0 && d->C > 0 && d->X > 0 &&
                     d->Y > 0 && d->Z > 0, "%s: bad sizes", who);
   SGV3D_REQUIRE(d->B <= 65535, "%s: B > 65535", who);
-  SGV3D_REQUIRE(d->D < 32768, "%s: D=%d too large", who, d->D);
+  SGV3D_REQUIRE(d->D <= 400, "%s: D=%d > 400 unsupported (height columns are staged in shared memory)", who, d->D);
   SGV3D_REQUIRE(d->C <= 256, "%s: C=%d > 256 unsupported by the fused path", who, d->C);
   SGV3D_REQUIRE((long long)d->X * d->Y < (long long)sort::kMaxHighBins << sort::kLowBits,
                 "%s: X*Y exceeds %d voxels per frame", who, sort::kMaxHighBins << sort::kLowBits);
   SGV3D_REQUIRE(d->arith >= SGV3D_ARITH_SEQ && d->arith <= SGV3D_ARITH_PAIR, "%s: bad arith", who);
   SGV3D_REQUIRE(d->ctx_dtype == SGV3D_DTYPE_F32 || d->ctx_dtype == SGV3D_DTYPE_BF16, "%s: bad ctx_dtype", who);
+  SGV3D_REQUIRE(d->height_is_logits == 0 || d->height_is_logits == 1, "%s: bad height_is_logits", who);
+  SGV3D_REQUIRE(d->height_batch_stride >= 0 && d->ctx_batch_stride >= 0 && d->grad_height_batch_stride >= 0 &&
+                    d->grad_ctx_batch_stride >= 0, "%s: negative batch stride", who);
   const long long slots = (long long)d->Nc * ceil_div(d->fH * d->fW, kChunk) * kChunk * d->D;
   SGV3D_REQUIRE(slots < (1ll << 31), "%s: more than 2^31 height-bin slots per frame", who);
   return SGV3D_OK;
@@ -510,6 +627,18 @@ int check_ws(const Workspace &w, void *ws, size_t bytes, const char *who) {
     set_error("%s: workspace %zu < required %zu bytes", who, bytes, w.bytes);
     return SGV3D_ERR_WORKSPACE_TOO_SMALL;
   }
+  return SGV3D_OK;
+}
+
+// 16-byte cp.async is legal when every (camera, bin, chunk) row start is 16-byte aligned
+bool columns_vec16(const float *base, long long batch_stride, int P) {
+  return (reinterpret_cast<uintptr_t>(base) % 16 == 0) && (batch_stride % 4 == 0) && (P % 4 == 0);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    SGV3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return SGV3D_OK;
 }
 
@@ -546,12 +675,23 @@ int transpose_context(const Dims &m, const Workspace &w, int ctx_dtype, const vo
   if (ctx_dtype == SGV3D_DTYPE_BF16)
     launch_transpose_pad<__nv_bfloat16, __nv_bfloat16>(
         static_cast<const __nv_bfloat16 *>(context), static_cast<__nv_bfloat16 *>(w.ctxT), batch, m.C,
-        m.P, m.P, (size_t)m.C * m.P, m.Cpad, (size_t)m.P * m.Cpad, s);
+        m.P, m.P, (size_t)m.cs, m.Cpad, (size_t)m.P * m.Cpad, s);
   else
     launch_transpose_pad<float, float>(static_cast<const float *>(context), static_cast<float *>(w.ctxT),
-                                       batch, m.C, m.P, m.P, (size_t)m.C * m.P, m.Cpad,
+                                       batch, m.C, m.P, m.P, (size_t)m.cs, m.Cpad,
                                        (size_t)m.P * m.Cpad, s);
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(context)");
+  return SGV3D_OK;
+}
+
+template <bool DST_SORTED>
+int launch_weights(const Dims &m, const Workspace &w, const float *height, float *dst, cudaStream_t s) {
+  dim3 gc(m.nchunks, m.B);
+  const size_t smem = sizeof(float) * m.D * kChunk;
+  if (int rc = set_smem(ls_weights_kernel<DST_SORTED>, smem)) return rc;
+  ls_weights_kernel<DST_SORTED><<<gc, kChunk, smem, s>>>(m, height, columns_vec16(height, m.hs, m.P) ? 1 : 0,
+                                                        w.run_cnt, w.run_d, w.run_dst, dst);
+  SGV3D_CHECK_LAUNCH("ls_weights_kernel");
   return SGV3D_OK;
 }
 
@@ -576,6 +716,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   if (desc->B == 0) return SGV3D_OK;
   SGV3D_REQUIRE(u_tab && v_tab && z_tab && ida_inv && m_virtual && m_ego && ref_heights && lower3 && size3,
                 "lift_splat_plan: null pointer");
+  SGV3D_REQUIRE(size3[0] > 0.f && size3[1] > 0.f && size3[2] > 0.f, "lift_splat_plan: voxel size must be > 0");
   const Dims m = make_dims(desc);
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan")) return rc;
@@ -584,6 +725,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   geom::Grid grid;
   for (int k = 0; k < 3; ++k) { grid.lower[k] = lower3[k]; grid.size[k] = size3[k]; }
   grid.X = m.X; grid.Y = m.Y; grid.Z = m.Z;
+  geom::z_thresholds(grid.size[2], m.Z, &grid.zt_lo, &grid.zt_hi);
 
   dim3 gc(m.nchunks, m.B);
   const size_t zsm = sizeof(float) * m.D;
@@ -605,7 +747,9 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   SGV3D_CHECK_LAUNCH("scan_hist_kernel(1)");
   ls_scatter_ell_kernel<<<gc, kChunk, 0, s>>>(m, w.run_cnt, w.run_vox, w.hist1, w.keys1, w.pay1);
   SGV3D_CHECK_LAUNCH("ls_scatter_ell_kernel");
-  dim3 g2(m.nblk2, m.B);
+  // the number of runs per frame lives on the device: size the second pass by a grid-stride loop
+  const int gx2 = m.nblk2 < 96 ? m.nblk2 : 96;
+  dim3 g2(gx2, m.B);
   sort::hist_contiguous_kernel<sort::kLowBits><<<g2, sort::kThreads, sizeof(int) * m.bins2, s>>>(
       w.keys1, (size_t)m.cap, w.count, 0, m.bins2, m.nblk2, w.hist2);
   SGV3D_CHECK_LAUNCH("hist_contiguous_kernel");
@@ -618,7 +762,8 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
           (size_t)m.cap);
   SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
   PlanFinalize fin{m, w.vm_pix, w.run_dst};
-  sort::row_ptr_kernel<PlanFinalize><<<dim3(ceil_div(m.cap, 256), m.B), 256, 0, s>>>(
+  const int gxr = ceil_div(m.cap, 256) < 256 ? ceil_div(m.cap, 256) : 256;
+  sort::row_ptr_kernel<PlanFinalize><<<dim3(gxr, m.B), 256, 0, s>>>(
       w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr, fin);
   SGV3D_CHECK_LAUNCH("row_ptr_kernel");
   return SGV3D_OK;
@@ -636,9 +781,7 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
-  dim3 gc(m.nchunks, m.B);
-  ls_weights_kernel<true><<<gc, kChunk, 0, s>>>(m, height, w.run_cnt, w.run_d, w.run_dst, w.w_vm);
-  SGV3D_CHECK_LAUNCH("ls_weights_kernel");
+  if (int rc = launch_weights<true>(m, w, height, w.w_vm, s)) return rc;
   if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
   return launch_reduce<float>(m, w, bev, s);
 }
@@ -661,17 +804,23 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   launch_transpose_pad<float, float>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
                                      (size_t)m.V * gpad, s);
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_bev)");
-  dim3 gc(m.nchunks, m.B);
-  ls_weights_kernel<false><<<gc, kChunk, 0, s>>>(m, height, w.run_cnt, w.run_d, w.run_dst, w.w_pm);
-  SGV3D_CHECK_LAUNCH("ls_weights_kernel");
+  if (int rc = launch_weights<false>(m, w, height, w.w_pm, s)) return rc;
   int rc = desc->ctx_dtype == SGV3D_DTYPE_BF16 ? launch_backward_gather<__nv_bfloat16>(m, w, gpad, s)
                                                 : launch_backward_gather<float>(m, w, gpad, s);
   if (rc) return rc;
-  ls_expand_kernel<false><<<gc, kChunk, 0, s>>>(m, w.run_cnt, w.run_d, w.run_vox, w.gw_pm, grad_height,
-                                                nullptr);
+  dim3 gc(m.nchunks, m.B);
+  if (m.logits) {
+    const size_t smem = sizeof(float) * m.D * kChunk;
+    if (int rc2 = set_smem(ls_expand_kernel<1>, smem)) return rc2;
+    ls_expand_kernel<1><<<gc, kChunk, smem, s>>>(m, height, columns_vec16(height, m.hs, m.P) ? 1 : 0, w.run_cnt,
+                                                 w.run_d, w.run_vox, w.w_pm, w.gw_pm, grad_height, nullptr);
+  } else {
+    ls_expand_kernel<0><<<gc, kChunk, 0, s>>>(m, nullptr, 0, w.run_cnt, w.run_d, w.run_vox, w.w_pm, w.gw_pm,
+                                              grad_height, nullptr);
+  }
   SGV3D_CHECK_LAUNCH("ls_expand_kernel");
   launch_transpose_pad<float, float>(w.gctxT, grad_context, m.B * m.Nc, m.P, m.C, gpad,
-                                     (size_t)m.P * gpad, m.P, (size_t)m.C * m.P, s);
+                                     (size_t)m.P * gpad, m.P, (size_t)m.gcs, s);
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_context)");
   return SGV3D_OK;
 }
@@ -687,8 +836,8 @@ extern "C" int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, i
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan_expand")) return rc;
   dim3 gc(m.nchunks, m.B);
   prof_begin(static_cast<cudaStream_t>(stream));
-  ls_expand_kernel<true><<<gc, kChunk, 0, static_cast<cudaStream_t>(stream)>>>(
-      m, w.run_cnt, w.run_d, w.run_vox, nullptr, nullptr, vox_out);
+  ls_expand_kernel<2><<<gc, kChunk, 0, static_cast<cudaStream_t>(stream)>>>(
+      m, nullptr, 0, w.run_cnt, w.run_d, w.run_vox, nullptr, nullptr, nullptr, vox_out);
   SGV3D_CHECK_LAUNCH("ls_expand_kernel(vox)");
   return SGV3D_OK;
 }

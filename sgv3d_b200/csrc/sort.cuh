@@ -84,24 +84,36 @@ scan_hist_kernel(int *__restrict__ hist, int bins, int nblk_max, const int *__re
 // Per-block digit histogram of a contiguous key array (used for the second pass, whose input
 // order only exists after the first scatter).
 // ---------------------------------------------------------------------------------------------
+// Blocks are visited with a grid-stride loop (gridDim.x may be far smaller than nblk_max: the item
+// count lives on the device, so the launch cannot be sized to it without a host sync).
 template <int SHIFT>
 __global__ void __launch_bounds__(kThreads)
 hist_contiguous_kernel(const int *__restrict__ keys, size_t frame_stride,
                        const int *__restrict__ n_items, int n_fixed, int bins, int nblk_max,
                        int *__restrict__ hist) {
   extern __shared__ int s_hist[];
-  const int frame = blockIdx.y, blk = blockIdx.x;
+  const int frame = blockIdx.y;
   const int n = n_items ? n_items[frame] : n_fixed;
-  const int begin = blk * kItemsPerBlock;
-  if (begin >= n) return;
-  for (int i = threadIdx.x; i < bins; i += kThreads) s_hist[i] = 0;
-  __syncthreads();
-  const int end = min(n, begin + kItemsPerBlock);
   const int *k = keys + (size_t)frame * frame_stride;
-  for (int i = begin + threadIdx.x; i < end; i += kThreads) atomicAdd(&s_hist[k[i] >> SHIFT], 1);
-  __syncthreads();
   int *h = hist + (size_t)frame * bins * nblk_max;
-  for (int i = threadIdx.x; i < bins; i += kThreads) h[(size_t)i * nblk_max + blk] = s_hist[i];
+  for (int blk = blockIdx.x; blk * kItemsPerBlock < n; blk += gridDim.x) {
+    const int begin = blk * kItemsPerBlock;
+    for (int i = threadIdx.x; i < bins; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int end = min(n, begin + kItemsPerBlock);
+    int kk[kItemsPerBlock / kThreads];
+#pragma unroll
+    for (int u = 0; u < kItemsPerBlock / kThreads; ++u) {
+      const int i = begin + u * kThreads + threadIdx.x;
+      kk[u] = (i < end) ? k[i] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kItemsPerBlock / kThreads; ++u)
+      if (kk[u] >= 0) atomicAdd(&s_hist[kk[u] >> SHIFT], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += kThreads) h[(size_t)i * nblk_max + blk] = s_hist[i];
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -124,9 +136,14 @@ __device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit
   __syncthreads();
   int *my = s_cnt + wid * bins;
   const int iters = in.iters(wid);
-  for (int it = 0; it < iters; ++it) {
-    int key, pay;
-    if (in.load(wid, it, lane, key, pay)) atomicAdd(&my[digit_of(key)], 1);
+  for (int it = 0; it < iters; it += 4) {  // 4 independent loads in flight per lane
+    int key[4], pay[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ok[u] = (it + u < iters) && in.load(wid, it + u, lane, key[u], pay[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ok[u]) atomicAdd(&my[digit_of(key[u])], 1);
   }
   __syncthreads();
   for (int d = t; d < bins; d += NWARPS * kWarp) {
@@ -140,25 +157,36 @@ __device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit
   }
   __syncthreads();
   const unsigned lt = lanemask_lt();
-  for (int it = 0; it < iters; ++it) {
-    int key = 0, pay = 0;
-    const bool valid = in.load(wid, it, lane, key, pay);
-    // invalid lanes get a private pseudo-digit so that they never match a real one
-    const int dig = valid ? digit_of(key) : (bins + lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, dig);
-    const int leader = __ffs(peers) - 1;
-    const int rank = __popc(peers & lt);
-    int base = 0;
-    if (valid && lane == leader) {
-      base = my[dig];
-      my[dig] = base + __popc(peers);
+  for (int it0 = 0; it0 < iters; it0 += 4) {
+    int key4[4], pay4[4];
+    bool ok4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      key4[u] = 0; pay4[u] = 0;
+      ok4[u] = (it0 + u < iters) && in.load(wid, it0 + u, lane, key4[u], pay4[u]);
     }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) {
-      out_keys[base + rank] = key;
-      out_payload[base + rank] = pay;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (it0 + u >= iters) break;  // warp-uniform
+      const bool valid = ok4[u];
+      const int key = key4[u], pay = pay4[u];
+      // invalid lanes get a private pseudo-digit so that they never match a real one
+      const int dig = valid ? digit_of(key) : (bins + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, dig);
+      const int leader = __ffs(peers) - 1;
+      const int rank = __popc(peers & lt);
+      int base = 0;
+      if (valid && lane == leader) {
+        base = my[dig];
+        my[dig] = base + __popc(peers);
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (valid) {
+        out_keys[base + rank] = key;
+        out_payload[base + rank] = pay;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -191,16 +219,18 @@ scatter_contiguous_kernel(const int *__restrict__ keys_in, const int *__restrict
                           int *__restrict__ keys_out, int *__restrict__ payload_out,
                           size_t frame_stride_out) {
   extern __shared__ int s_cnt[];
-  const int frame = blockIdx.y, blk = blockIdx.x;
+  const int frame = blockIdx.y;
   const int n = n_items ? n_items[frame] : n_fixed;
-  if (blk * kItemsPerBlock >= n) return;
-  ContiguousInput in{keys_in + (size_t)frame * frame_stride_in,
-                     payload_in ? payload_in + (size_t)frame * frame_stride_in : nullptr,
-                     blk * kItemsPerBlock, n};
-  stable_scatter_block<kWarps>(in, DigitOf<SHIFT, MASK>(), bins,
-                               gbase + (size_t)frame * bins * nblk_max, nblk_max, blk, s_cnt,
-                               keys_out + (size_t)frame * frame_stride_out,
-                               payload_out + (size_t)frame * frame_stride_out);
+  for (int blk = blockIdx.x; blk * kItemsPerBlock < n; blk += gridDim.x) {
+    ContiguousInput in{keys_in + (size_t)frame * frame_stride_in,
+                       payload_in ? payload_in + (size_t)frame * frame_stride_in : nullptr,
+                       blk * kItemsPerBlock, n};
+    stable_scatter_block<kWarps>(in, DigitOf<SHIFT, MASK>(), bins,
+                                 gbase + (size_t)frame * bins * nblk_max, nblk_max, blk, s_cnt,
+                                 keys_out + (size_t)frame * frame_stride_out,
+                                 payload_out + (size_t)frame * frame_stride_out);
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,18 +245,20 @@ row_ptr_kernel(const int *__restrict__ keys, size_t frame_stride, const int *__r
   const int n = n_items ? n_items[frame] : n_fixed;
   const int *k = keys + (size_t)frame * frame_stride;
   int *rp = row_ptr + (size_t)frame * (V + 1);
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  const int j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (n == 0) {
-    for (int v = j; v <= V; v += gridDim.x * blockDim.x) rp[v] = 0;
+    for (int v = j0; v <= V; v += stride) rp[v] = 0;
     return;
   }
-  if (j >= n) return;
-  const int key = min(k[j], V);
-  const int prev = (j > 0) ? min(k[j - 1], V) : -1;
-  for (int v = prev + 1; v <= key; ++v) rp[v] = j;
-  if (j == n - 1)
-    for (int v = key + 1; v <= V; ++v) rp[v] = n;
-  fin(frame, j);
+  for (int j = j0; j < n; j += stride) {
+    const int key = min(k[j], V);
+    const int prev = (j > 0) ? min(k[j - 1], V) : -1;
+    for (int v = prev + 1; v <= key; ++v) rp[v] = j;
+    if (j == n - 1)
+      for (int v = key + 1; v <= V; ++v) rp[v] = n;
+    fin(frame, j);
+  }
 }
 
 }  // namespace sort

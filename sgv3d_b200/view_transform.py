@@ -55,12 +55,19 @@ def build_frustum(final_dim: Sequence[int], downsample_factor: int, d_bound: Seq
     return torch.stack((u, v, z, torch.ones_like(z)), -1)
 
 
+def _inverse(x: torch.Tensor) -> torch.Tensor:
+    """``torch.inverse`` without its host synchronisation: ``linalg.inv_ex`` is the routine
+    ``torch.inverse`` / ``Tensor.inverse`` dispatch to, minus the ``info`` check that forces a
+    device->host copy (bit-identical results; tests/test_gpu_lift_splat.py checks that)."""
+    return torch.linalg.inv_ex(x, check_errors=False).inverse
+
+
 def camera_matrices(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat):
     """``ida.inverse()``, ``sensor2virtual @ inverse(intrin)``, ``sensor2ego @ inverse(sensor2virtual)``
-    evaluated with the reference's own torch calls (lss_fpn.py:392,361,367), shapes (B, Nc, 4, 4)."""
-    ida_inv = ida_mat.inverse()
-    m_virtual = sensor2virtual_mat.matmul(torch.inverse(intrin_mat))
-    m_ego = sensor2ego_mat.matmul(torch.inverse(sensor2virtual_mat))
+    evaluated with the reference's own torch routines (lss_fpn.py:392,361,367), shapes (B, Nc, 4, 4)."""
+    ida_inv = _inverse(ida_mat)
+    m_virtual = sensor2virtual_mat.matmul(_inverse(intrin_mat))
+    m_ego = sensor2ego_mat.matmul(_inverse(sensor2virtual_mat))
     return ida_inv, m_virtual, m_ego
 
 
@@ -70,42 +77,57 @@ def _f32c(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+class _GridConst:
+    """Host-side constants that never change for a module: frustum axes on the device and the
+    quantisation lower bound / voxel size as host floats (reading them from CUDA buffers every call
+    would synchronise, as lss_fpn.py:487-491 does)."""
+
+    def __init__(self, frustum, voxel_coord, voxel_size, device):
+        fr = frustum.to(device)
+        self.D, self.fH, self.fW = (int(s) for s in fr.shape[:3])
+        # the three axes of the frustum buffer; looked up, never recomputed (SURVEY.md §8 a2)
+        self.u = fr[0, 0, :, 0].contiguous()
+        self.v = fr[0, :, 0, 1].contiguous()
+        self.z = fr[:, 0, 0, 2].contiguous()
+        # lss_fpn.py:487-488: lower = voxel_coord - voxel_size / 2.0 in fp32 tensor arithmetic
+        vc, vs = voxel_coord.detach().float().cpu(), voxel_size.detach().float().cpu()
+        self.lower = N.host_f32x3((vc - vs / 2.0).tolist())
+        self.size = N.host_f32x3(vs.tolist())
+        self.device = device
+
+
 class _Geometry:
     """Device-resident operands of the per-point geometry for one batch of cameras."""
 
     def __init__(self, frustum, sensor2ego, sensor2virtual, intrin, ida, reference_heights, bda,
-                 voxel_coord, voxel_size):
+                 voxel_coord, voxel_size, grid_const: Optional[_GridConst] = None):
         dev = sensor2ego.device
         if dev.type != "cuda":
             raise RuntimeError("sgv3d_b200 runs on CUDA tensors only (no CPU fallback)")
         self.device = dev
         self.B, self.Nc = int(sensor2ego.shape[0]), int(sensor2ego.shape[1])
-        self.D, self.fH, self.fW = (int(s) for s in frustum.shape[:3])
-        fr = frustum.to(dev)
-        # the three axes of the frustum buffer; looked up, never recomputed (SURVEY.md §8 a2)
-        self.u = fr[0, 0, :, 0].contiguous()
-        self.v = fr[0, :, 0, 1].contiguous()
-        self.z = fr[:, 0, 0, 2].contiguous()
+        gc = grid_const if grid_const is not None and grid_const.device == dev else \
+            _GridConst(frustum, voxel_coord, voxel_size, dev)
+        self.gc = gc
+        self.D, self.fH, self.fW = gc.D, gc.fH, gc.fW
         ida_inv, m_virtual, m_ego = camera_matrices(sensor2ego, sensor2virtual, intrin, ida)
         self.ida_inv, self.m_virtual, self.m_ego = (_f32c(t, dev) for t in (ida_inv, m_virtual, m_ego))
         self.ref_h = _f32c(reference_heights, dev).reshape(-1)
         self.bda = _f32c(bda, dev)
-        # lss_fpn.py:487-488: lower = voxel_coord - voxel_size / 2.0 in fp32 tensor arithmetic
-        vc, vs = voxel_coord.detach().float().cpu(), voxel_size.detach().float().cpu()
-        self.lower = N.host_f32x3((vc - vs / 2.0).tolist())
-        self.size = N.host_f32x3(vs.tolist())
 
     def pointer_args(self):
-        return [N.ptr(self.u), N.ptr(self.v), N.ptr(self.z), N.ptr(self.ida_inv), N.ptr(self.m_virtual),
-                N.ptr(self.m_ego), N.ptr(self.bda), N.ptr(self.ref_h), self.lower, self.size]
+        gc = self.gc
+        return [N.ptr(gc.u), N.ptr(gc.v), N.ptr(gc.z), N.ptr(self.ida_inv), N.ptr(self.m_virtual),
+                N.ptr(self.m_ego), N.ptr(self.bda), N.ptr(self.ref_h), gc.lower, gc.size]
 
 
 def geometry_indices(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
-                     bda_mat, voxel_coord, voxel_size, arith: Optional[int] = None, return_xyz: bool = False):
+                     bda_mat, voxel_coord, voxel_size, arith: Optional[int] = None, return_xyz: bool = False,
+                     grid_const: "Optional[_GridConst]" = None):
     """int32 (B, Nc, D, fH, fW, 3) voxel indices == ``((get_geometry(...) - lower) / size).int()``
     (lss_fpn.py:478-488), computed by one kernel; optionally also the fp32 ego coordinates."""
     g = _Geometry(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
-                  bda_mat, voxel_coord, voxel_size)
+                  bda_mat, voxel_coord, voxel_size, grid_const)
     idx = torch.empty(g.B, g.Nc, g.D, g.fH, g.fW, 3, dtype=torch.int32, device=g.device)
     xyz = torch.empty(idx.shape, dtype=torch.float32, device=g.device) if return_xyz else None
     with torch.cuda.device(g.device):
@@ -113,6 +135,15 @@ def geometry_indices(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, id
             default_arith() if arith is None else arith, g.B, g.Nc, g.D, g.fH, g.fW, *g.pointer_args(),
             N.ptr(idx), N.ptr(xyz), N.current_stream()))
     return (idx, xyz) if return_xyz else idx
+
+
+def _camera_block_stride(t: torch.Tensor, channels: int, fh: int, fw: int, what: str) -> int:
+    """Element stride between consecutive cameras of a (BN, channels, fH, fW) tensor whose per-camera
+    block is dense (a contiguous tensor, or a channel slice of the height net's output)."""
+    assert tuple(t.shape[1:]) == (channels, fh, fw), (what, tuple(t.shape), (channels, fh, fw))
+    if t.shape[0] > 0 and t.stride()[1:] != (fh * fw, fw, 1):
+        raise RuntimeError(f"{what}: per-camera [C][fH][fW] block must be dense, got strides {t.stride()}")
+    return int(t.stride(0)) if t.shape[0] > 1 else channels * fh * fw
 
 
 class LiftSplatPlan:
@@ -123,9 +154,10 @@ class LiftSplatPlan:
 
     def __init__(self, frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
                  bda_mat, voxel_coord, voxel_size, voxel_num: Sequence[int], channels: int,
-                 ctx_dtype: torch.dtype = torch.float32, arith: Optional[int] = None):
+                 ctx_dtype: torch.dtype = torch.float32, arith: Optional[int] = None,
+                 grid_const: Optional[_GridConst] = None):
         g = _Geometry(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
-                      bda_mat, voxel_coord, voxel_size)
+                      bda_mat, voxel_coord, voxel_size, grid_const)
         self.geometry = g
         self.device = g.device
         if ctx_dtype not in (torch.float32, torch.bfloat16):
@@ -148,23 +180,42 @@ class LiftSplatPlan:
             N.check(N.lib().sgv3d_lift_splat_plan(self.desc, *g.pointer_args(), N.ptr(self.ws), self.ws_bytes,
                                                   N.current_stream()))
 
-    # -- raw entry points (no autograd) -------------------------------------------------------------
-    def forward(self, height: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+    def _call_desc(self, height, context, logits, g_height=None, g_ctx=None) -> "N.LiftSplatDesc":
         d = self.desc
         self._check_inputs(height, context)
+        c = N.LiftSplatDesc.from_buffer_copy(d)
+        c.height_is_logits = 1 if logits else 0
+        c.height_batch_stride = _camera_block_stride(height, d.D, d.fH, d.fW, "height")
+        c.ctx_batch_stride = _camera_block_stride(context, d.C, d.fH, d.fW, "context")
+        if g_height is not None:
+            c.grad_height_batch_stride = _camera_block_stride(g_height, d.D, d.fH, d.fW, "grad_height")
+            c.grad_ctx_batch_stride = _camera_block_stride(g_ctx, d.C, d.fH, d.fW, "grad_context")
+        return c
+
+    # -- raw entry points (no autograd) -------------------------------------------------------------
+    def forward(self, height: torch.Tensor, context: torch.Tensor, logits: bool = False) -> torch.Tensor:
+        """``height``: probabilities (or raw logits with ``logits=True``: the softmax over D is fused)."""
+        d = self._call_desc(height, context, logits)
         bev = torch.empty(d.B, d.C, d.Y, d.X, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             N.check(N.lib().sgv3d_lift_splat_forward(d, N.ptr(height), N.ptr(context), N.ptr(bev), N.ptr(self.ws),
                                                      self.ws_bytes, N.current_stream()))
         return bev
 
-    def backward(self, grad_bev: torch.Tensor, height: torch.Tensor, context: torch.Tensor):
-        d = self.desc
-        self._check_inputs(height, context)
+    def backward(self, grad_bev: torch.Tensor, height: torch.Tensor, context: torch.Tensor, logits: bool = False,
+                 out_height: Optional[torch.Tensor] = None, out_context: Optional[torch.Tensor] = None):
+        """Gradients w.r.t. ``height`` (w.r.t. the logits when ``logits=True``) and ``context``; optionally
+        written straight into caller-provided (possibly strided) buffers."""
         g = grad_bev.float().contiguous()
-        assert g.shape == (d.B, d.C, d.Y, d.X)
-        g_height = torch.empty_like(height)
-        g_ctx = torch.empty(context.shape, dtype=torch.float32, device=self.device)
+        d0 = self.desc
+        assert tuple(g.shape) == (d0.B, d0.C, d0.Y, d0.X)
+        bn = d0.B * d0.Nc
+        g_height = out_height if out_height is not None else \
+            torch.empty(bn, d0.D, d0.fH, d0.fW, dtype=torch.float32, device=self.device)
+        g_ctx = out_context if out_context is not None else \
+            torch.empty(bn, d0.C, d0.fH, d0.fW, dtype=torch.float32, device=self.device)
+        assert g_height.dtype == torch.float32 and g_ctx.dtype == torch.float32
+        d = self._call_desc(height, context, logits, g_height, g_ctx)
         with torch.cuda.device(self.device):
             N.check(N.lib().sgv3d_lift_splat_backward(d, N.ptr(g), N.ptr(height), N.ptr(context), N.ptr(g_height),
                                                       N.ptr(g_ctx), N.ptr(self.ws), self.ws_bytes,
@@ -185,7 +236,6 @@ class LiftSplatPlan:
         bn = d.B * d.Nc
         if not (height.is_cuda and context.is_cuda):
             raise RuntimeError("height and context must be CUDA tensors")
-        assert height.is_contiguous() and context.is_contiguous()
         if height.dtype != torch.float32:
             raise RuntimeError(f"expected height of dtype float32, got {height.dtype}")
         if context.dtype != self.ctx_dtype:
@@ -194,26 +244,55 @@ class LiftSplatPlan:
         assert tuple(context.shape) == (bn, d.C, d.fH, d.fW), (tuple(context.shape), (bn, d.C, d.fH, d.fW))
 
 
+def _dense_blocks(t: torch.Tensor) -> torch.Tensor:
+    """Return ``t`` itself when every camera's [C][fH][fW] block is dense (e.g. a channel slice of the
+    height net's output), else a contiguous copy."""
+    return t if t.stride()[1:] == (t.shape[2] * t.shape[3], t.shape[3], 1) else t.contiguous()
+
+
 class _LiftSplatFunction(Function):
     @staticmethod
-    def forward(ctx, height, context, plan: LiftSplatPlan):
-        height = height.contiguous()
-        context = context.contiguous()
-        ctx.plan = plan
+    def forward(ctx, height, context, plan: LiftSplatPlan, logits: bool):
+        height, context = _dense_blocks(height), _dense_blocks(context)
+        ctx.plan, ctx.logits = plan, logits
         ctx.save_for_backward(height, context)
-        return plan.forward(height, context)
+        return plan.forward(height, context, logits)
 
     @staticmethod
     def backward(ctx, grad_bev):
         height, context = ctx.saved_tensors
-        g_height, g_ctx = ctx.plan.backward(grad_bev, height, context)
-        return g_height, g_ctx.to(context.dtype), None
+        g_height, g_ctx = ctx.plan.backward(grad_bev, height, context, ctx.logits)
+        return g_height, g_ctx.to(context.dtype), None, None
 
 
-def lift_splat(height: torch.Tensor, context: torch.Tensor, plan: LiftSplatPlan) -> torch.Tensor:
+class _LiftSplatHeadFunction(Function):
+    """Whole LSSFPN call site on the height net's output tensor (BN, D + C, fH, fW): height logits and
+    context are consumed in place (no slicing copies) and the gradient is written straight into one
+    (BN, D + C, fH, fW) buffer (no ``cat``)."""
+
+    @staticmethod
+    def forward(ctx, height_feature, plan: LiftSplatPlan, d: int, c: int):
+        hf = height_feature if height_feature.is_contiguous() else height_feature.contiguous()
+        ctx.plan, ctx.dc = plan, (d, c)
+        ctx.save_for_backward(hf)
+        return plan.forward(hf[:, :d], hf[:, d:d + c], logits=True)
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        (hf,) = ctx.saved_tensors
+        d, c = ctx.dc
+        g = torch.empty_like(hf) if hf.shape[1] == d + c else torch.zeros_like(hf)
+        ctx.plan.backward(grad_bev, hf[:, :d], hf[:, d:d + c], logits=True,
+                          out_height=g[:, :d], out_context=g[:, d:d + c])
+        return g, None, None, None
+
+
+def lift_splat(height: torch.Tensor, context: torch.Tensor, plan: LiftSplatPlan, logits: bool = False) -> torch.Tensor:
     """(B, C, Y, X) fp32 contiguous BEV map: ``voxel_pooling(idx, (height (x) context) permuted)``
-    of lss_fpn.py:464-495 without the frustum tensor.  Differentiable w.r.t. height and context."""
-    return _LiftSplatFunction.apply(height, context, plan)
+    of lss_fpn.py:464-495 without the frustum tensor.  ``height`` holds the softmax-ed height-bin
+    probabilities, or the raw logits with ``logits=True`` (softmax of lss_fpn.py:462 fused).
+    Differentiable w.r.t. height and context."""
+    return _LiftSplatFunction.apply(height, context, plan, logits)
 
 
 class LiftSplat(nn.Module):
@@ -243,6 +322,13 @@ class LiftSplat(nn.Module):
         # host copies, so that no call has to read a CUDA scalar (lss_fpn.py:491 syncs every call)
         self._grid = tuple(int(v) for v in self.voxel_num.tolist())
         self._plan_cache: Dict[tuple, LiftSplatPlan] = {}
+        self._grid_const: Optional[_GridConst] = None
+
+    def _const(self, device) -> _GridConst:
+        gc = self._grid_const
+        if gc is None or gc.device != device:
+            gc = self._grid_const = _GridConst(self.frustum, self.voxel_coord, self.voxel_size, device)
+        return gc
 
     # -- geometry -----------------------------------------------------------------------------------
     def get_geometry(self, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights, bda_mat):
@@ -272,7 +358,7 @@ class LiftSplat(nn.Module):
             if key in self._plan_cache:
                 return self._plan_cache[key]
         plan = LiftSplatPlan(self.frustum, *args, self.voxel_coord, self.voxel_size, self._grid, c, ctx_dtype,
-                             self.arith)
+                             self.arith, grid_const=self._const(args[0].device))
         if key is not None:
             self._plan_cache = {key: plan}
         return plan
@@ -282,20 +368,20 @@ class LiftSplat(nn.Module):
         """LSSFPN: ``height_feature`` = (B*Nc, D + C, fH, fW) output of the height net
         (lss_fpn.py:461).  Returns the (B, C, Y, X) contiguous BEV map of lss_fpn.py:494-495."""
         d, c = self.height_channels, self.output_channels
-        height = height_feature[:, :d].softmax(1)                               # lss_fpn.py:462
-        context = height_feature[:, d:d + c]                                    # lss_fpn.py:464-466
         plan = self.make_plan(mats_dict, sweep_index, c)
-        return lift_splat(height.float(), context.float(), plan)
+        # softmax over the D logits (lss_fpn.py:462), lift (:464-466), geometry (:478-488) and pooling
+        # (:490-495) all happen inside the library, on the head's output tensor in place
+        return _LiftSplatHeadFunction.apply(height_feature.float(), plan, d, c)
 
     def forward_single_sweep_bsm(self, height_logits, semantic_logits, context, mats_dict,
                                  sweep_index: int = 0) -> torch.Tensor:
         """BSMLSSFPN: ``out[0], out[1], out[2]`` of the MSCT head (bsm_lss_fpn.py:522-529): height
         logits (BN, D, fH, fW), 7 semantic logits, 80 context channels.  The 87-channel masked context
         is assembled exactly as the reference does, then lifted and splatted."""
-        height = height_logits.softmax(dim=1)                                   # bsm_lss_fpn.py:523
-        semantic = semantic_logits.softmax(dim=1)                               # :524
+        semantic = semantic_logits.softmax(dim=1)                               # bsm_lss_fpn.py:524
         tran_feat = torch.cat((context, semantic), dim=1)                       # :526
         mask = semantic[:, 0, :, :].unsqueeze(1) > 0.45                         # :528 background
         tran_feat = tran_feat * (1 - mask.int())                                # :529
         plan = self.make_plan(mats_dict, sweep_index, int(tran_feat.shape[1]))
-        return lift_splat(height.float(), tran_feat.float(), plan)
+        # height softmax (bsm_lss_fpn.py:523) fused into the kernels
+        return lift_splat(height_logits.float(), tran_feat.float(), plan, logits=True)

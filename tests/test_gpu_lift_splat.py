@@ -164,3 +164,41 @@ def test_fused_equals_op_level_path():
     feat = O.lift(height, ctx).reshape(2, 1, shape.channels, shape.D, shape.fH, shape.fW).permute(0, 1, 3, 4, 5, 2)
     bev_op = voxel_pooling(torch.from_numpy(idx).cuda(), feat.contiguous().cuda(), list(shape.grid)).contiguous()
     torch.testing.assert_close(bev, bev_op, rtol=RTOL, atol=ATOL)
+
+
+def test_inverse_without_host_sync_is_bit_identical():
+    """camera_matrices uses linalg.inv_ex (no info check => no host sync); it must give the very bits
+    torch.inverse / Tensor.inverse give, because those 16 floats feed the bit-exact geometry."""
+    from sgv3d_b200.view_transform import _inverse
+    shape = get_shape("dair_r50")
+    m = make_mats(shape, 64, 2, seed=77, bda="random")
+    for key in ("sensor2ego", "sensor2virtual", "intrin", "ida"):
+        x = m[key].cuda()
+        assert torch.equal(_inverse(x), torch.inverse(x)), key
+        assert torch.equal(_inverse(x), x.inverse()), key
+
+
+def test_fused_softmax_on_strided_head_output():
+    """logits=True (softmax over D fused, forward and backward) on channel-slice views of a wider
+    (BN, D + C + extra, fH, fW) tensor == torch softmax + the probability path on contiguous copies."""
+    from sgv3d_b200 import lift_splat
+    shape, plan, idx, _, _ = _setup("rope3d_r50", 2, 1, 36, "identity")
+    D, C = shape.D, shape.channels
+    g = torch.Generator(device="cuda").manual_seed(3)
+    big = torch.randn(2, D + C + 5, shape.fH, shape.fW, device="cuda", generator=g)
+    big[:, :D] *= 3.0
+    a = big.clone().requires_grad_(True)
+    bev_a = lift_splat(a[:, :D], a[:, D:D + C], plan, logits=True)
+    b = big.clone().requires_grad_(True)
+    bev_b = lift_splat(b[:, :D].softmax(1).contiguous(), b[:, D:D + C].contiguous(), plan)
+    torch.testing.assert_close(bev_a, bev_b, rtol=1e-5, atol=1e-5)
+    gb = torch.randn(bev_a.shape, device="cuda", generator=g)
+    bev_a.backward(gb)
+    bev_b.backward(gb)
+    torch.testing.assert_close(a.grad[:, D:D + C], b.grad[:, D:D + C], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(a.grad[:, :D], b.grad[:, :D], rtol=1e-4, atol=1e-5)
+    assert float(a.grad[:, D + C:].abs().max()) == 0.0
+    # fp64 anchor for the fused-softmax forward
+    want = CO.lift_splat_forward64(idx, big[:, :D].double().softmax(1).float().cpu().numpy(),
+                                   big[:, D:D + C].cpu().numpy(), *shape.grid)
+    np.testing.assert_allclose(bev_a.detach().cpu().numpy(), want, rtol=RTOL, atol=ATOL)
