@@ -39,6 +39,7 @@ struct Grid {
   // zt_lo / zt_hi are found on the host by bisection over float bit patterns with the same IEEE
   // division (RN(t/s) is monotone in t).  NaN passes both tests, as cvt.rzi(NaN) = 0 is in range.
   float zt_lo, zt_hi;
+  float rcp_size[2];  // RN(1 / size.x), RN(1 / size.y) for the guarded fast quantisation
 };
 
 template <int ARITH>
@@ -171,11 +172,25 @@ struct PixelRay {
     }
     const float tz = __fsub_rn(gz, g.lower[2]);
     if (tz <= g.zt_lo || tz >= g.zt_hi) return -1;
-    const int ix = __float2int_rz(__fdiv_rn(__fsub_rn(gx, g.lower[0]), g.size[0]));
+    const int ix = quantize_guarded(gx, g.lower[0], g.size[0], g.rcp_size[0]);
     if ((unsigned)ix >= (unsigned)g.X) return -1;
-    const int iy = __float2int_rz(__fdiv_rn(__fsub_rn(gy, g.lower[1]), g.size[1]));
+    const int iy = quantize_guarded(gy, g.lower[1], g.size[1], g.rcp_size[1]);
     if ((unsigned)iy >= (unsigned)g.Y) return -1;
     return iy * g.X + ix;
+  }
+
+  // trunc(RN((g - lower) / size)) without the IEEE division in the common case.
+  // q = RN(t * RN(1/size)) differs from the true quotient Q by at most |Q| * (2^-23 + 2^-48), and the
+  // reference value RN(Q) by at most |Q| * 2^-24.  If no integer lies within |q| * 2^-22 of q, both fall
+  // strictly between the same two consecutive integers and truncate identically; otherwise (and for
+  // zero / non-finite / integer-valued q) the exact division decides.
+  static __device__ __forceinline__ int quantize_guarded(float gcoord, float lower, float size, float rcp) {
+    const float t = __fsub_rn(gcoord, lower);
+    const float q = __fmul_rn(t, rcp);
+    const float k = rintf(q);
+    if (fabsf(__fsub_rn(q, k)) > __fmul_rn(fabsf(q), 2.384185791015625e-07f))  // 2^-22
+      return __float2int_rz(q);
+    return __float2int_rz(__fdiv_rn(t, size));
   }
 };
 

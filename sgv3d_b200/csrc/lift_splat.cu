@@ -16,9 +16,9 @@
 //     transpose_pad_kernel    context NCHW -> one 16B-aligned row per pixel
 //     ls_weights_kernel       [softmax over D fused] w[run] = sum_{d in run} p[d,pixel]; the height
 //                             columns of 128 pixels are staged in smem with cp.async (all loads in flight)
-//     ls_reduce_kernel        per 32-voxel strip: entries staged in smem, per voxel
-//                             sum_j w[j] * ctx_row[pixel_j] in sorted (deterministic) order,
-//                             written NCHW-coalesced incl. zero rows
+//     ls_reduce_kernel        one warp per 8-voxel strip (no block barriers): per voxel
+//                             sum_j w[j] * ctx_row[pixel_j] in sorted (deterministic) order, 8 row
+//                             loads in flight, written as 32-byte sectors of the NCHW output
 //   BACKWARD (values; pixel-major, no sort needed)
 //     transpose_pad_kernel    grad_bev NCHW -> one row per voxel
 //     ls_weights_kernel       w per run (pixel-major destination)
@@ -119,7 +119,7 @@ __device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t)
 // Pure ALU work (no global reads besides three tiny tables); two bins per iteration for ILP.
 // ---------------------------------------------------------------------------------------------
 template <int ARITH>
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kChunk, 6)
 ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__restrict__ v_tab,
                     const float *__restrict__ z_tab, const float *__restrict__ ida_inv,
                     const float *__restrict__ mv, const float *__restrict__ me,
@@ -212,23 +212,31 @@ ls_scatter_ell_kernel(Dims m, const int *__restrict__ run_cnt, const int *__rest
   in.warp_max = __reduce_max_sync(0xffffffffu, in.cnt);
   sort::stable_scatter_block<kChunk / 32>(in, sort::DigitOf<0, sort::kLowBins - 1>(), sort::kLowBins,
                                           gbase1 + (size_t)b * sort::kLowBins * m.nchunks, m.nchunks,
-                                          chunk, s_cnt, keys1 + (size_t)b * m.cap,
-                                          pay1 + (size_t)b * m.cap);
+                                          chunk, s_cnt,
+                                          sort::PlaceKeyPayload{keys1 + (size_t)b * m.cap, pay1 + (size_t)b * m.cap});
 }
 
-// PLAN 3/3 epilogue functor: inverse permutation + frame-local pixel id per sorted run.
-struct PlanFinalize {
-  Dims m;
-  int *pay2_to_pix;  // in: ELL slot, out: frame-local pixel (n*P + p)
-  int *run_dst;
-  __device__ __forceinline__ void operator()(int frame, int j) const {
-    int *pp = pay2_to_pix + (size_t)frame * m.cap;
-    const int slot = pp[j];
-    run_dst[(size_t)frame * m.cap + slot] = j;
+// PLAN 3/3: placement functor of the second radix pass.  Besides the sorted key it records, per
+// sorted position, the frame-local pixel id (n*P + p) of the run, and the inverse permutation
+// (ELL slot -> sorted position) that the forward weights pass scatters through.
+struct PlanPlace {
+  int *keys2, *vm_pix, *run_dst;
+  int D, cpc, P;
+  __device__ __forceinline__ void operator()(int pos, int key, int slot) const {
+    keys2[pos] = key;
+    run_dst[slot] = pos;
     const int t = slot & (kChunk - 1);
-    const int chunk = (slot / kChunk) / m.D;
-    const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
-    pp[j] = n * m.P + ci * kChunk + t;
+    const int chunk = (slot / kChunk) / D;
+    const int n = chunk / cpc, ci = chunk - n * cpc;
+    vm_pix[pos] = n * P + ci * kChunk + t;
+  }
+};
+struct PlanPlaceFactory {
+  int *keys2, *vm_pix, *run_dst;
+  int D, cpc, P, cap;
+  __device__ __forceinline__ PlanPlace operator()(int frame) const {
+    const size_t o = (size_t)frame * cap;
+    return PlanPlace{keys2 + o, vm_pix + o, run_dst + o, D, cpc, P};
   }
 };
 
@@ -265,19 +273,21 @@ __device__ __forceinline__ void stage_columns(float *col, const float *__restric
   __syncthreads();
 }
 
-// In-place softmax over D of this thread's staged column (matches torch.softmax within fp32
-// rounding: exp(x - max) / sum).  col holds probabilities afterwards.
-__device__ __forceinline__ void softmax_column(float *col, int D, int t) {
+// Softmax over D of this thread's staged column (torch.softmax within fp32 rounding:
+// exp(x - max) / sum).  Leaves the un-normalised exponentials in col and returns 1 / sum, so the
+// normalisation costs one multiply per run / per output instead of a pass over the column.
+__device__ __forceinline__ float softmax_column(float *col, int D, int t) {
   float mx = -INFINITY;
+#pragma unroll 4
   for (int d = 0; d < D; ++d) mx = fmaxf(mx, col[d * kChunk + t]);
   float sum = 0.0f;
+#pragma unroll 4
   for (int d = 0; d < D; ++d) {
     const float e = expf(__fsub_rn(col[d * kChunk + t], mx));
     col[d * kChunk + t] = e;
     sum = __fadd_rn(sum, e);
   }
-  const float inv = __fdiv_rn(1.0f, sum);
-  for (int d = 0; d < D; ++d) col[d * kChunk + t] = __fmul_rn(col[d * kChunk + t], inv);
+  return __fdiv_rn(1.0f, sum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -299,7 +309,7 @@ ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
   if (p0 + t >= m.P) return;
   const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
   if (cnt == 0) return;
-  if (m.logits) softmax_column(col, m.D, t);
+  const float scale = m.logits ? softmax_column(col, m.D, t) : 1.0f;
   // batch the (strided) run descriptors 4 at a time
   for (int r0 = 0; r0 < cnt; r0 += 4) {
     int packed[4], dst[4];
@@ -319,7 +329,7 @@ ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
         float acc = 0.0f;
         for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
         const size_t o = DST_SORTED ? (size_t)b * m.cap + dst[u] : ell_slot(frame_chunk, m.D, r0 + u, t);
-        w_out[o] = acc;
+        w_out[o] = m.logits ? __fmul_rn(acc, scale) : acc;
       }
     }
   }
@@ -350,105 +360,118 @@ struct RowLoad<__nv_bfloat16> {
   }
 };
 
-constexpr int kTileV = 32;
-constexpr int kStage = 1024;  // entries staged per round (8 KB)
+constexpr int kStripV = 8;        // voxels per warp task: one 32-byte sector of every channel plane
+constexpr int kReduceWarps = 8;   // warps per CTA (independent tasks; no block-level barrier)
 constexpr int kRowsInFlight = 8;
 
+// One warp owns kStripV consecutive voxels.  It reads their CSR offsets, streams the strip's sorted
+// (pixel, weight) entries 32 at a time (register + shuffle broadcast, next 32 prefetched), keeps 8
+// independent 128-bit context-row loads in flight regardless of voxel boundaries, accumulates the
+// current voxel in registers (lanes own 4-channel slices) and flushes it to a private smem tile at
+// every voxel boundary.  Finally the [C][8] tile is written as 32-byte sectors of the NCHW output.
 template <typename CT, int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReduceWarps * 32)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
                  const int *__restrict__ vm_pix, const float *__restrict__ w_vm,
                  float *__restrict__ bev) {
-  extern __shared__ float tile[];  // [C][kTileV + 1]
-  __shared__ int s_rp[kTileV + 1];
-  __shared__ int s_pix[kStage];
-  __shared__ float s_w[kStage];
+  extern __shared__ float tiles[];  // [kReduceWarps][C][kStripV + 1]
   const int b = blockIdx.y;
-  const int v0 = blockIdx.x * kTileV;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int *rp = row_ptr + (size_t)b * (m.V + 1);
-  const int vend = min(v0 + kTileV, m.V);
-  const int nv = vend - v0;
-  float *out = bev + (size_t)b * m.C * m.V;
-  if (tid <= kTileV) s_rp[tid] = rp[min(v0 + tid, vend)];
-  __syncthreads();
-  const int tile_lo = s_rp[0], tile_hi = s_rp[nv];
-  if (tile_lo == tile_hi) {  // empty strip: zero rows only
-    for (int c = wid; c < m.C; c += 8)
-      if (lane < nv) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, 0.0f);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int v0 = (blockIdx.x * kReduceWarps + wid) * kStripV;
+  if (v0 >= m.V) return;
+  const int nv = min(kStripV, m.V - v0);
+  float *tile = tiles + (size_t)wid * m.C * (kStripV + 1);
+  float *out = bev + (size_t)b * m.C * m.V + v0;
+  const int *rp = row_ptr + (size_t)b * (m.V + 1) + v0;
+  const int my_rp = rp[min(lane, nv)];          // lanes 0..nv hold the strip's CSR offsets
+  const int lo = __shfl_sync(0xffffffffu, my_rp, 0), hi = __shfl_sync(0xffffffffu, my_rp, nv);
+  const int nslices = m.Cpad / 4;
+
+  if (lo == hi) {  // empty strip: zero sectors only
+    for (int i = lane; i < m.C * kStripV; i += 32) {
+      const int c = i / kStripV, j = i - c * kStripV;
+      if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, 0.0f);
+    }
     return;
   }
-  const int nslices = m.Cpad / 4;
   const CT *rows = ctxT + (size_t)b * m.Nc * m.P * m.Cpad;
   const int *pix = vm_pix + (size_t)b * m.cap;
   const float *wv = w_vm + (size_t)b * m.cap;
 
-  float acc[4][NCH][4];  // the warp's 4 voxels
+  float acc[NCH][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int k = 0; k < NCH; ++k)
 #pragma unroll
-    for (int k = 0; k < NCH; ++k)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][k][e] = 0.0f;
+    for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
+  int vi = 0;                                              // voxel currently accumulated
+  int next_b = __shfl_sync(0xffffffffu, my_rp, 1);         // first entry of voxel vi + 1
 
-  for (int base = tile_lo; base < tile_hi; base += kStage) {
-    const int stage_hi = min(base + kStage, tile_hi);
-    if (base != tile_lo) __syncthreads();
-    for (int j = base + tid; j < stage_hi; j += 256) {
-      s_pix[j - base] = pix[j];
-      s_w[j - base] = wv[j];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int vl = wid * 4 + i;
-      if (vl < nv) {  // warp-uniform
-        const int lo = max(s_rp[vl], base), hi = min(s_rp[vl + 1], stage_hi);
-        for (int q = lo; q < hi; q += kRowsInFlight) {
-          float r[kRowsInFlight][NCH][4];
-          float ww[kRowsInFlight];
-#pragma unroll
-          for (int u = 0; u < kRowsInFlight; ++u) {
-            if (q + u < hi) {  // warp-uniform predicate: no dummy arithmetic on padding entries
-              const CT *row = rows + (size_t)s_pix[q + u - base] * m.Cpad;
-              ww[u] = s_w[q + u - base];
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) {
-                const int sl = k * 32 + lane;
-                if (sl < nslices) RowLoad<CT>::load(row, sl, r[u][k]);
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kRowsInFlight; ++u) {
-            if (q + u < hi) {
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) {
-                if (k * 32 + lane < nslices) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) acc[i][k][e] = __fmaf_rn(ww[u], r[u][k][e], acc[i][k][e]);
-                }
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int vl = wid * 4 + i;
+  auto flush = [&]() {  // store the finished voxel's channels, restart the accumulator
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = (k * 32 + lane) * 4 + e;
-        if (c < m.C) tile[c * (kTileV + 1) + vl] = acc[i][k][e];
+        if (c < m.C) tile[c * (kStripV + 1) + vi] = acc[k][e];
+        acc[k][e] = 0.0f;
       }
+    ++vi;
+    next_b = __shfl_sync(0xffffffffu, my_rp, min(vi + 1, nv));
+  };
+
+  int cur_pix = 0;
+  float cur_w = 0.0f;
+  if (lo + lane < hi) {
+    cur_pix = pix[lo + lane];
+    cur_w = wv[lo + lane];
   }
-  __syncthreads();
-  for (int c = wid; c < m.C; c += 8)
-    if (lane < nv) stg_stream_f1(out + (size_t)c * m.V + v0 + lane, tile[c * (kTileV + 1) + lane]);
+  for (int base = lo; base < hi; base += 32) {
+    const int cnt = min(32, hi - base);
+    int nxt_pix = 0;
+    float nxt_w = 0.0f;
+    if (base + 32 + lane < hi) {  // prefetch the next 32 entries
+      nxt_pix = pix[base + 32 + lane];
+      nxt_w = wv[base + 32 + lane];
+    }
+    for (int q = 0; q < cnt; q += kRowsInFlight) {
+      float r[kRowsInFlight][NCH][4];
+      float ww[kRowsInFlight];
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        const int src = min(q + u, cnt - 1);
+        const CT *row = rows + (size_t)__shfl_sync(0xffffffffu, cur_pix, src) * m.Cpad;
+        ww[u] = __shfl_sync(0xffffffffu, cur_w, src);
+        if (q + u < cnt) {
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const int sl = k * 32 + lane;
+            if (sl < nslices) RowLoad<CT>::load(row, sl, r[u][k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        if (q + u < cnt) {                       // warp-uniform
+          while (base + q + u >= next_b) flush();  // warp-uniform: entry belongs to a later voxel
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            if (k * 32 + lane < nslices) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(ww[u], r[u][k][e], acc[k][e]);
+            }
+          }
+        }
+      }
+    }
+    cur_pix = nxt_pix;
+    cur_w = nxt_w;
+  }
+  while (vi < nv) flush();  // last voxel with entries + trailing empty voxels
+  __syncwarp();
+  for (int i = lane; i < m.C * kStripV; i += 32) {
+    const int c = i / kStripV, j = i - c * kStripV;
+    if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, tile[c * (kStripV + 1) + j]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -565,9 +588,9 @@ ls_expand_kernel(Dims m, const float *__restrict__ height, int vec16, const int 
   if (MODE == 1) stage_columns(col, height + (size_t)(b * m.Nc + n) * m.hs, m.D, m.P, p0, vec16 != 0);
   if (p >= m.P) return;
   const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
-  float S = 0.0f;
+  float S = 0.0f, scale = 1.0f;
   if (MODE == 1) {
-    softmax_column(col, m.D, t);
+    scale = softmax_column(col, m.D, t);
     for (int r = 0; r < cnt; ++r) {
       const size_t s = ell_slot(frame_chunk, m.D, r, t);
       S = __fmaf_rn(w_pm[s], gw_pm[s], S);
@@ -588,7 +611,7 @@ ls_expand_kernel(Dims m, const float *__restrict__ height, int vec16, const int 
     if (MODE == 2) vox_out[base + (size_t)d * m.P] = in ? vv : -1;
     else if (MODE == 1)
       stg_stream_f1(g_height + base + (size_t)d * m.P,
-                    __fmul_rn(col[d * kChunk + t], __fsub_rn(in ? gv : 0.0f, S)));
+                    __fmul_rn(__fmul_rn(col[d * kChunk + t], scale), __fsub_rn(in ? gv : 0.0f, S)));
     else stg_stream_f1(g_height + base + (size_t)d * m.P, in ? gv : 0.0f);
     if (d + 1 == d1) {
       if (++r < cnt) {
@@ -644,13 +667,16 @@ int set_smem(K kernel, size_t bytes) {
 
 template <typename CT>
 int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
-  dim3 grid(ceil_div(m.V, kTileV), m.B);
-  const size_t smem = sizeof(float) * m.C * (kTileV + 1);
+  dim3 grid(ceil_div(ceil_div(m.V, kStripV), kReduceWarps), m.B);
+  const size_t smem = sizeof(float) * kReduceWarps * m.C * (kStripV + 1);
   const CT *ctxT = static_cast<const CT *>(w.ctxT);
-  if (m.Cpad <= 128)
-    ls_reduce_kernel<CT, 1><<<grid, 256, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
-  else
-    ls_reduce_kernel<CT, 2><<<grid, 256, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
+  if (m.Cpad <= 128) {
+    if (int rc = set_smem(ls_reduce_kernel<CT, 1>, smem)) return rc;
+    ls_reduce_kernel<CT, 1><<<grid, kReduceWarps * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
+  } else {
+    if (int rc = set_smem(ls_reduce_kernel<CT, 2>, smem)) return rc;
+    ls_reduce_kernel<CT, 2><<<grid, kReduceWarps * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
+  }
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
 }
@@ -726,6 +752,8 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   for (int k = 0; k < 3; ++k) { grid.lower[k] = lower3[k]; grid.size[k] = size3[k]; }
   grid.X = m.X; grid.Y = m.Y; grid.Z = m.Z;
   geom::z_thresholds(grid.size[2], m.Z, &grid.zt_lo, &grid.zt_hi);
+  grid.rcp_size[0] = 1.0f / grid.size[0];  // IEEE single division on the host: correctly rounded
+  grid.rcp_size[1] = 1.0f / grid.size[1];
 
   dim3 gc(m.nchunks, m.B);
   const size_t zsm = sizeof(float) * m.D;
@@ -756,15 +784,13 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   sort::scan_hist_kernel<<<m.B, sort::kScanThreads, 0, s>>>(w.hist2, m.bins2, m.nblk2, w.count,
                                                             sort::kItemsPerBlock, nullptr);
   SGV3D_CHECK_LAUNCH("scan_hist_kernel(2)");
-  sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF>
+  sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF, PlanPlaceFactory>
       <<<g2, sort::kThreads, sizeof(int) * sort::kWarps * m.bins2, s>>>(
-          w.keys1, w.pay1, (size_t)m.cap, w.count, 0, m.bins2, w.hist2, m.nblk2, w.keys2, w.vm_pix,
-          (size_t)m.cap);
+          w.keys1, w.pay1, (size_t)m.cap, w.count, 0, m.bins2, w.hist2, m.nblk2,
+          PlanPlaceFactory{w.keys2, w.vm_pix, w.run_dst, m.D, m.cpc, m.P, m.cap});
   SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
-  PlanFinalize fin{m, w.vm_pix, w.run_dst};
-  const int gxr = ceil_div(m.cap, 256) < 256 ? ceil_div(m.cap, 256) : 256;
-  sort::row_ptr_kernel<PlanFinalize><<<dim3(gxr, m.B), 256, 0, s>>>(
-      w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr, fin);
+  const int gxr = ceil_div(m.cap, 256) < 128 ? ceil_div(m.cap, 256) : 128;
+  sort::row_ptr_kernel<<<dim3(gxr, m.B), 256, 0, s>>>(w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr);
   SGV3D_CHECK_LAUNCH("row_ptr_kernel");
   return SGV3D_OK;
 }

@@ -125,12 +125,20 @@ hist_contiguous_kernel(const int *__restrict__ keys, size_t frame_stride,
 // Phase B: cross-warp exclusive scan per digit, then match-any ranking with warp-private running
 //          counters => position is a pure function of the canonical order.
 // ---------------------------------------------------------------------------------------------
-template <int NWARPS, typename In, typename DigitFn>
+// Default placement: write (key, payload) at the item's sorted position.
+struct PlaceKeyPayload {
+  int *keys, *payload;
+  __device__ __forceinline__ void operator()(int pos, int key, int pay) const {
+    keys[pos] = key;
+    payload[pos] = pay;
+  }
+};
+
+template <int NWARPS, typename In, typename DigitFn, typename Place>
 __device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit_of, int bins,
                                                      const int *__restrict__ gbase_frame,
                                                      int nblk_max, int blk, int *s_cnt /*[NWARPS][bins]*/,
-                                                     int *__restrict__ out_keys,
-                                                     int *__restrict__ out_payload) {
+                                                     const Place &place) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   for (int i = t; i < NWARPS * bins; i += NWARPS * kWarp) s_cnt[i] = 0;
   __syncthreads();
@@ -181,10 +189,7 @@ __device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit
         my[dig] = base + __popc(peers);
       }
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (valid) {
-        out_keys[base + rank] = key;
-        out_payload[base + rank] = pay;
-      }
+      if (valid) place(base + rank, key, pay);
       __syncwarp();
     }
   }
@@ -211,36 +216,39 @@ struct DigitOf {
   __device__ __forceinline__ int operator()(int key) const { return (key >> SHIFT) & MASK; }
 };
 
-template <int SHIFT, int MASK>
+// PlaceFactory(frame) -> Place functor for that frame.
+template <int SHIFT, int MASK, typename PlaceFactory>
 __global__ void __launch_bounds__(kThreads)
 scatter_contiguous_kernel(const int *__restrict__ keys_in, const int *__restrict__ payload_in,
                           size_t frame_stride_in, const int *__restrict__ n_items, int n_fixed,
-                          int bins, const int *__restrict__ gbase, int nblk_max,
-                          int *__restrict__ keys_out, int *__restrict__ payload_out,
-                          size_t frame_stride_out) {
+                          int bins, const int *__restrict__ gbase, int nblk_max, PlaceFactory make_place) {
   extern __shared__ int s_cnt[];
   const int frame = blockIdx.y;
   const int n = n_items ? n_items[frame] : n_fixed;
+  const auto place = make_place(frame);
   for (int blk = blockIdx.x; blk * kItemsPerBlock < n; blk += gridDim.x) {
     ContiguousInput in{keys_in + (size_t)frame * frame_stride_in,
                        payload_in ? payload_in + (size_t)frame * frame_stride_in : nullptr,
                        blk * kItemsPerBlock, n};
     stable_scatter_block<kWarps>(in, DigitOf<SHIFT, MASK>(), bins,
-                                 gbase + (size_t)frame * bins * nblk_max, nblk_max, blk, s_cnt,
-                                 keys_out + (size_t)frame * frame_stride_out,
-                                 payload_out + (size_t)frame * frame_stride_out);
+                                 gbase + (size_t)frame * bins * nblk_max, nblk_max, blk, s_cnt, place);
     __syncthreads();
   }
 }
 
+struct PlaceKeyPayloadFactory {
+  int *keys, *payload;
+  size_t frame_stride;
+  __device__ __forceinline__ PlaceKeyPayload operator()(int frame) const {
+    return PlaceKeyPayload{keys + (size_t)frame * frame_stride, payload + (size_t)frame * frame_stride};
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // row_ptr[v] = first sorted position whose key >= v, for v in [0, V]; keys sorted ascending.
-// Also applies `fin(j, payload)` per sorted item (used to build the inverse permutation).
-// ---------------------------------------------------------------------------------------------
-template <typename Fin>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256) static
 row_ptr_kernel(const int *__restrict__ keys, size_t frame_stride, const int *__restrict__ n_items,
-               int n_fixed, int V, int *__restrict__ row_ptr /*[frame][V+1]*/, Fin fin) {
+               int n_fixed, int V, int *__restrict__ row_ptr /*[frame][V+1]*/) {
   const int frame = blockIdx.y;
   const int n = n_items ? n_items[frame] : n_fixed;
   const int *k = keys + (size_t)frame * frame_stride;
@@ -257,7 +265,6 @@ row_ptr_kernel(const int *__restrict__ keys, size_t frame_stride, const int *__r
     for (int v = prev + 1; v <= key; ++v) rp[v] = j;
     if (j == n - 1)
       for (int v = key + 1; v <= V; ++v) rp[v] = n;
-    fin(frame, j);
   }
 }
 

@@ -76,10 +76,6 @@ vp_prepare_kernel(int N, int X, int Y, int Z, const int32_t *__restrict__ geom,
     h[(size_t)i * nblk + blk] = s_hist[i];
 }
 
-struct NoFin {
-  __device__ __forceinline__ void operator()(int, int) const {}
-};
-
 // ---- reduce: one warp per voxel ---------------------------------------------------------------
 // VEC = 4: C % 4 == 0, lanes own float4 slices (row base is 16-byte aligned).  VEC = 1: any C.
 // NCH = number of VEC-wide slices per lane = ceil(C / (32*VEC)).
@@ -240,9 +236,10 @@ extern "C" int sgv3d_voxel_pooling_forward(int B, int N, int C, int X, int Y, in
   sort::scan_hist_kernel<<<B, sort::kScanThreads, 0, s>>>(w.hist1, sort::kLowBins, w.nblk, nullptr,
                                                           sort::kItemsPerBlock, nullptr);
   SGV3D_CHECK_LAUNCH("scan_hist_kernel(1)");
-  sort::scatter_contiguous_kernel<0, sort::kLowBins - 1>
+  sort::scatter_contiguous_kernel<0, sort::kLowBins - 1, sort::PlaceKeyPayloadFactory>
       <<<gb, sort::kThreads, sizeof(int) * sort::kWarps * sort::kLowBins, s>>>(
-          w.keys0, nullptr, (size_t)N, nullptr, N, sort::kLowBins, w.hist1, w.nblk, w.keys1, w.pay1, (size_t)N);
+          w.keys0, nullptr, (size_t)N, nullptr, N, sort::kLowBins, w.hist1, w.nblk,
+          sort::PlaceKeyPayloadFactory{w.keys1, w.pay1, (size_t)N});
   SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(1)");
   sort::hist_contiguous_kernel<sort::kLowBits><<<gb, sort::kThreads, sizeof(int) * w.bins2, s>>>(
       w.keys1, (size_t)N, nullptr, N, w.bins2, w.nblk, w.hist2);
@@ -250,12 +247,13 @@ extern "C" int sgv3d_voxel_pooling_forward(int B, int N, int C, int X, int Y, in
   sort::scan_hist_kernel<<<B, sort::kScanThreads, 0, s>>>(w.hist2, w.bins2, w.nblk, nullptr,
                                                           sort::kItemsPerBlock, nullptr);
   SGV3D_CHECK_LAUNCH("scan_hist_kernel(2)");
-  sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF>
+  sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF, sort::PlaceKeyPayloadFactory>
       <<<gb, sort::kThreads, sizeof(int) * sort::kWarps * w.bins2, s>>>(
-          w.keys1, w.pay1, (size_t)N, nullptr, N, w.bins2, w.hist2, w.nblk, w.keys2, w.pay2, (size_t)N);
+          w.keys1, w.pay1, (size_t)N, nullptr, N, w.bins2, w.hist2, w.nblk,
+          sort::PlaceKeyPayloadFactory{w.keys2, w.pay2, (size_t)N});
   SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
-  sort::row_ptr_kernel<NoFin><<<dim3(ceil_div(N, 256), B), 256, 0, s>>>(w.keys2, (size_t)N, nullptr, N, V,
-                                                                      w.row_ptr, NoFin());
+  sort::row_ptr_kernel<<<dim3(ceil_div(N, 256) < 512 ? ceil_div(N, 256) : 512, B), 256, 0, s>>>(
+      w.keys2, (size_t)N, nullptr, N, V, w.row_ptr);
   SGV3D_CHECK_LAUNCH("row_ptr_kernel");
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(features) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
   if (vec) {
