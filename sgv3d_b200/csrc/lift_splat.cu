@@ -38,6 +38,13 @@ namespace {
 
 constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
 
+// Sorted (voxel-major) entry: element offset of the pixel's context row inside the frame's
+// channels-last copy (written by the plan), and the run weight (written by the forward weights pass).
+struct __align__(8) Entry {
+  int off;
+  float w;
+};
+
 struct Dims {
   int B, Nc, D, fH, fW, C, X, Y, Z;
   int P;        // fH*fW pixels per camera
@@ -53,9 +60,9 @@ struct Dims {
 };
 
 struct Workspace {
-  int *count, *run_cnt, *run_vox, *run_d, *run_dst, *hist1, *keys1, *pay1, *hist2, *keys2,
-      *vm_pix, *row_ptr;
-  float *w_vm, *w_pm, *gw_pm, *gT, *gctxT;
+  int *count, *run_cnt, *run_vox, *run_d, *run_dst, *hist1, *keys1, *pay1, *hist2, *keys2, *row_ptr;
+  Entry *vm_ent;  // sorted (row offset, weight) pairs
+  float *w_pm, *gw_pm, *gT, *gctxT;
   void *ctxT;
   size_t bytes;
 };
@@ -95,9 +102,8 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   w.pay1 = c.take<int>(slots);
   w.hist2 = c.take<int>(B * m.bins2 * m.nblk2);
   w.keys2 = c.take<int>(slots);
-  w.vm_pix = c.take<int>(slots);
+  w.vm_ent = reinterpret_cast<Entry *>(c.take<int2>(slots));
   w.row_ptr = c.take<int>(B * (m.V + 1));
-  w.w_vm = c.take<float>(slots);
   w.w_pm = c.take<float>(slots);
   w.gw_pm = c.take<float>(slots);
   const size_t rows = B * m.Nc * m.P;
@@ -119,7 +125,7 @@ __device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t)
 // Pure ALU work (no global reads besides three tiny tables); two bins per iteration for ILP.
 // ---------------------------------------------------------------------------------------------
 template <int ARITH>
-__global__ void __launch_bounds__(kChunk, 6)
+__global__ void __launch_bounds__(kChunk, 5)
 ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__restrict__ v_tab,
                     const float *__restrict__ z_tab, const float *__restrict__ ida_inv,
                     const float *__restrict__ mv, const float *__restrict__ me,
@@ -217,26 +223,30 @@ ls_scatter_ell_kernel(Dims m, const int *__restrict__ run_cnt, const int *__rest
 }
 
 // PLAN 3/3: placement functor of the second radix pass.  Besides the sorted key it records, per
-// sorted position, the frame-local pixel id (n*P + p) of the run, and the inverse permutation
+// sorted position, the context-row offset of the run's pixel, and the inverse permutation
 // (ELL slot -> sorted position) that the forward weights pass scatters through.
 struct PlanPlace {
-  int *keys2, *vm_pix, *run_dst;
-  int D, cpc, P;
+  int *keys2;
+  Entry *vm_ent;
+  int *run_dst;
+  int D, cpc, P, Cpad;
   __device__ __forceinline__ void operator()(int pos, int key, int slot) const {
     keys2[pos] = key;
     run_dst[slot] = pos;
     const int t = slot & (kChunk - 1);
     const int chunk = (slot / kChunk) / D;
     const int n = chunk / cpc, ci = chunk - n * cpc;
-    vm_pix[pos] = n * P + ci * kChunk + t;
+    vm_ent[pos].off = (n * P + ci * kChunk + t) * Cpad;
   }
 };
 struct PlanPlaceFactory {
-  int *keys2, *vm_pix, *run_dst;
-  int D, cpc, P, cap;
+  int *keys2;
+  Entry *vm_ent;
+  int *run_dst;
+  int D, cpc, P, Cpad, cap;
   __device__ __forceinline__ PlanPlace operator()(int frame) const {
     const size_t o = (size_t)frame * cap;
-    return PlanPlace{keys2 + o, vm_pix + o, run_dst + o, D, cpc, P};
+    return PlanPlace{keys2 + o, vm_ent + o, run_dst + o, D, cpc, P, Cpad};
   }
 };
 
@@ -298,7 +308,8 @@ template <bool DST_SORTED>
 __global__ void __launch_bounds__(kChunk)
 ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
                   const int *__restrict__ run_cnt, const int *__restrict__ run_d,
-                  const int *__restrict__ run_dst, float *__restrict__ w_out) {
+                  const int *__restrict__ run_dst, float *__restrict__ w_pm_out,
+                  Entry *__restrict__ vm_ent_out) {
   extern __shared__ float col[];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
@@ -328,8 +339,9 @@ ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
         const int d0 = packed[u] & 0xffff, d1 = packed[u] >> 16;
         float acc = 0.0f;
         for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-        const size_t o = DST_SORTED ? (size_t)b * m.cap + dst[u] : ell_slot(frame_chunk, m.D, r0 + u, t);
-        w_out[o] = m.logits ? __fmul_rn(acc, scale) : acc;
+        const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
+        if (DST_SORTED) vm_ent_out[(size_t)b * m.cap + dst[u]].w = wgt;
+        else w_pm_out[ell_slot(frame_chunk, m.D, r0 + u, t)] = wgt;
       }
     }
   }
@@ -346,6 +358,7 @@ template <typename CT>
 struct RowLoad;
 template <>
 struct RowLoad<float> {
+  // `row` may already include the lane's slice offset; `slice` is an additional 4-element slice index
   static __device__ __forceinline__ void load(const float *row, int slice, float (&v)[4]) {
     const float4 t = __ldg(reinterpret_cast<const float4 *>(row) + slice);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -360,116 +373,98 @@ struct RowLoad<__nv_bfloat16> {
   }
 };
 
-constexpr int kStripV = 8;        // voxels per warp task: one 32-byte sector of every channel plane
-constexpr int kReduceWarps = 8;   // warps per CTA (independent tasks; no block-level barrier)
-constexpr int kRowsInFlight = 8;
+constexpr int kStripV = 8;  // voxels per CTA == warps per CTA: one 32-byte sector of every channel plane
 
-// One warp owns kStripV consecutive voxels.  It reads their CSR offsets, streams the strip's sorted
-// (pixel, weight) entries 32 at a time (register + shuffle broadcast, next 32 prefetched), keeps 8
-// independent 128-bit context-row loads in flight regardless of voxel boundaries, accumulates the
-// current voxel in registers (lanes own 4-channel slices) and flushes it to a private smem tile at
-// every voxel boundary.  Finally the [C][8] tile is written as 32-byte sectors of the NCHW output.
+// CTA = strip of 8 consecutive voxels, warp i accumulates voxel v0 + i:
+//   out[c, v] = sum_j w_j * ctx_row[pixel_j][c]   over the voxel's sorted (deterministic) entry list.
+// Entries are fetched 32 at a time with one coalesced 8-byte load per lane and broadcast from a
+// per-warp smem slot (no shuffles, no divergence bookkeeping); the inner loop is LDS.64 + LDG.128 +
+// 4 FFMA per entry with four independent row loads in flight; lanes own 4-channel slices.
+// One block barrier, then the [C][8] tile leaves as full 32-byte sectors of the NCHW planes.
 template <typename CT, int NCH>
-__global__ void __launch_bounds__(kReduceWarps * 32)
+__global__ void __launch_bounds__(kStripV * 32)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
-                 const int *__restrict__ vm_pix, const float *__restrict__ w_vm,
-                 float *__restrict__ bev) {
-  extern __shared__ float tiles[];  // [kReduceWarps][C][kStripV + 1]
+                 const Entry *__restrict__ vm_ent, float *__restrict__ bev) {
+  extern __shared__ float tile[];            // [C][kStripV + 1]
+  __shared__ Entry s_ent[kStripV][32];
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int v0 = (blockIdx.x * kReduceWarps + wid) * kStripV;
-  if (v0 >= m.V) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int v0 = blockIdx.x * kStripV;
+  const int v = v0 + wid;
   const int nv = min(kStripV, m.V - v0);
-  float *tile = tiles + (size_t)wid * m.C * (kStripV + 1);
+  int lo = 0, hi = 0;
+  if (v < m.V) {
+    const int *rp = row_ptr + (size_t)b * (m.V + 1) + v;
+    lo = rp[0];
+    hi = rp[1];
+  }
   float *out = bev + (size_t)b * m.C * m.V + v0;
-  const int *rp = row_ptr + (size_t)b * (m.V + 1) + v0;
-  const int my_rp = rp[min(lane, nv)];          // lanes 0..nv hold the strip's CSR offsets
-  const int lo = __shfl_sync(0xffffffffu, my_rp, 0), hi = __shfl_sync(0xffffffffu, my_rp, nv);
-  const int nslices = m.Cpad / 4;
-
-  if (lo == hi) {  // empty strip: zero sectors only
-    for (int i = lane; i < m.C * kStripV; i += 32) {
-      const int c = i / kStripV, j = i - c * kStripV;
+  if (!__syncthreads_or(hi > lo)) {  // empty strip: zero sectors only
+    for (int i = tid; i < m.C * kStripV; i += kStripV * 32) {
+      const int c = i >> 3, j = i & 7;
       if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, 0.0f);
     }
     return;
   }
-  const CT *rows = ctxT + (size_t)b * m.Nc * m.P * m.Cpad;
-  const int *pix = vm_pix + (size_t)b * m.cap;
-  const float *wv = w_vm + (size_t)b * m.cap;
-
+  const int nslices = m.Cpad / 4;
   float acc[NCH][4];
 #pragma unroll
   for (int k = 0; k < NCH; ++k)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
-  int vi = 0;                                              // voxel currently accumulated
-  int next_b = __shfl_sync(0xffffffffu, my_rp, 1);         // first entry of voxel vi + 1
 
-  auto flush = [&]() {  // store the finished voxel's channels, restart the accumulator
+  if (hi > lo) {
+    const CT *rows_lane = ctxT + (size_t)b * m.Nc * m.P * m.Cpad + lane * 4;  // this lane's slice 0
+    const Entry *ent = vm_ent + (size_t)b * m.cap;
+    Entry *mine = s_ent[wid];
+    for (int base = lo; base < hi; base += 32) {
+      const int cnt = min(32, hi - base);
+      __syncwarp();
+      if (lane < cnt) mine[lane] = ent[base + lane];
+      __syncwarp();
+      int q = 0;
+      for (; q + 4 <= cnt; q += 4) {
+        Entry en[4];
+        float r[4][NCH][4];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k)
+        for (int u = 0; u < 4; ++u) {
+          en[u] = mine[q + u];  // LDS.64 broadcast
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = (k * 32 + lane) * 4 + e;
-        if (c < m.C) tile[c * (kStripV + 1) + vi] = acc[k][e];
-        acc[k][e] = 0.0f;
-      }
-    ++vi;
-    next_b = __shfl_sync(0xffffffffu, my_rp, min(vi + 1, nv));
-  };
-
-  int cur_pix = 0;
-  float cur_w = 0.0f;
-  if (lo + lane < hi) {
-    cur_pix = pix[lo + lane];
-    cur_w = wv[lo + lane];
-  }
-  for (int base = lo; base < hi; base += 32) {
-    const int cnt = min(32, hi - base);
-    int nxt_pix = 0;
-    float nxt_w = 0.0f;
-    if (base + 32 + lane < hi) {  // prefetch the next 32 entries
-      nxt_pix = pix[base + 32 + lane];
-      nxt_w = wv[base + 32 + lane];
-    }
-    for (int q = 0; q < cnt; q += kRowsInFlight) {
-      float r[kRowsInFlight][NCH][4];
-      float ww[kRowsInFlight];
-#pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u) {
-        const int src = min(q + u, cnt - 1);
-        const CT *row = rows + (size_t)__shfl_sync(0xffffffffu, cur_pix, src) * m.Cpad;
-        ww[u] = __shfl_sync(0xffffffffu, cur_w, src);
-        if (q + u < cnt) {
-#pragma unroll
-          for (int k = 0; k < NCH; ++k) {
-            const int sl = k * 32 + lane;
-            if (sl < nslices) RowLoad<CT>::load(row, sl, r[u][k]);
-          }
+          for (int k = 0; k < NCH; ++k)
+            if (k * 32 + lane < nslices) RowLoad<CT>::load(rows_lane + en[u].off, k * 32, r[u][k]);
         }
-      }
 #pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u) {
-        if (q + u < cnt) {                       // warp-uniform
-          while (base + q + u >= next_b) flush();  // warp-uniform: entry belongs to a later voxel
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int k = 0; k < NCH; ++k) {
+          for (int k = 0; k < NCH; ++k)
             if (k * 32 + lane < nslices) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(ww[u], r[u][k][e], acc[k][e]);
+              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(en[u].w, r[u][k][e], acc[k][e]);
             }
+      }
+      for (; q < cnt; ++q) {
+        const Entry en = mine[q];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          if (k * 32 + lane < nslices) {
+            float r1[4];
+            RowLoad<CT>::load(rows_lane + en.off, k * 32, r1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(en.w, r1[e], acc[k][e]);
           }
-        }
       }
     }
-    cur_pix = nxt_pix;
-    cur_w = nxt_w;
   }
-  while (vi < nv) flush();  // last voxel with entries + trailing empty voxels
-  __syncwarp();
-  for (int i = lane; i < m.C * kStripV; i += 32) {
-    const int c = i / kStripV, j = i - c * kStripV;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = (k * 32 + lane) * 4 + e;
+      if (c < m.C) tile[c * (kStripV + 1) + wid] = acc[k][e];
+    }
+  __syncthreads();
+  for (int i = tid; i < m.C * kStripV; i += kStripV * 32) {
+    const int c = i >> 3, j = i & 7;
     if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, tile[c * (kStripV + 1) + j]);
   }
 }
@@ -667,16 +662,13 @@ int set_smem(K kernel, size_t bytes) {
 
 template <typename CT>
 int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
-  dim3 grid(ceil_div(ceil_div(m.V, kStripV), kReduceWarps), m.B);
-  const size_t smem = sizeof(float) * kReduceWarps * m.C * (kStripV + 1);
+  dim3 grid(ceil_div(m.V, kStripV), m.B);
+  const size_t smem = sizeof(float) * m.C * (kStripV + 1);
   const CT *ctxT = static_cast<const CT *>(w.ctxT);
-  if (m.Cpad <= 128) {
-    if (int rc = set_smem(ls_reduce_kernel<CT, 1>, smem)) return rc;
-    ls_reduce_kernel<CT, 1><<<grid, kReduceWarps * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
-  } else {
-    if (int rc = set_smem(ls_reduce_kernel<CT, 2>, smem)) return rc;
-    ls_reduce_kernel<CT, 2><<<grid, kReduceWarps * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_pix, w.w_vm, bev);
-  }
+  if (m.Cpad <= 128)
+    ls_reduce_kernel<CT, 1><<<grid, kStripV * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_ent, bev);
+  else
+    ls_reduce_kernel<CT, 2><<<grid, kStripV * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_ent, bev);
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
 }
@@ -711,12 +703,12 @@ int transpose_context(const Dims &m, const Workspace &w, int ctx_dtype, const vo
 }
 
 template <bool DST_SORTED>
-int launch_weights(const Dims &m, const Workspace &w, const float *height, float *dst, cudaStream_t s) {
+int launch_weights(const Dims &m, const Workspace &w, const float *height, cudaStream_t s) {
   dim3 gc(m.nchunks, m.B);
   const size_t smem = sizeof(float) * m.D * kChunk;
   if (int rc = set_smem(ls_weights_kernel<DST_SORTED>, smem)) return rc;
   ls_weights_kernel<DST_SORTED><<<gc, kChunk, smem, s>>>(m, height, columns_vec16(height, m.hs, m.P) ? 1 : 0,
-                                                        w.run_cnt, w.run_d, w.run_dst, dst);
+                                                        w.run_cnt, w.run_d, w.run_dst, w.w_pm, w.vm_ent);
   SGV3D_CHECK_LAUNCH("ls_weights_kernel");
   return SGV3D_OK;
 }
@@ -787,7 +779,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF, PlanPlaceFactory>
       <<<g2, sort::kThreads, sizeof(int) * sort::kWarps * m.bins2, s>>>(
           w.keys1, w.pay1, (size_t)m.cap, w.count, 0, m.bins2, w.hist2, m.nblk2,
-          PlanPlaceFactory{w.keys2, w.vm_pix, w.run_dst, m.D, m.cpc, m.P, m.cap});
+          PlanPlaceFactory{w.keys2, w.vm_ent, w.run_dst, m.D, m.cpc, m.P, m.Cpad, m.cap});
   SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
   const int gxr = ceil_div(m.cap, 256) < 128 ? ceil_div(m.cap, 256) : 128;
   sort::row_ptr_kernel<<<dim3(gxr, m.B), 256, 0, s>>>(w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr);
@@ -807,7 +799,7 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
-  if (int rc = launch_weights<true>(m, w, height, w.w_vm, s)) return rc;
+  if (int rc = launch_weights<true>(m, w, height, s)) return rc;
   if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
   return launch_reduce<float>(m, w, bev, s);
 }
@@ -830,7 +822,7 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   launch_transpose_pad<float, float>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
                                      (size_t)m.V * gpad, s);
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_bev)");
-  if (int rc = launch_weights<false>(m, w, height, w.w_pm, s)) return rc;
+  if (int rc = launch_weights<false>(m, w, height, s)) return rc;
   int rc = desc->ctx_dtype == SGV3D_DTYPE_BF16 ? launch_backward_gather<__nv_bfloat16>(m, w, gpad, s)
                                                 : launch_backward_gather<float>(m, w, gpad, s);
   if (rc) return rc;
