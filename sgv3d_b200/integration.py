@@ -1,0 +1,75 @@
+"""Swap the lift-splat half of an existing reference backbone for the fused sm_100a path, without
+editing the reference sources.
+
+``patch_view_transform(backbone)`` rebinds ``_forward_single_sweep`` on an ``LSSFPN``
+(layers/backbones/lss_fpn.py:421-495) or ``BSMLSSFPN`` (layers/backbones/bsm_lss_fpn.py:485-559) instance.
+Everything up to and including the height net stays the module's own code (``get_cam_feats``,
+``assist_layer``, ``_forward_height_net``); everything after it -- height softmax, lift, ``get_geometry``,
+quantisation, ``voxel_pooling``, ``.contiguous()`` -- is replaced by one ``LiftSplat`` call built around the
+module's own registered buffers.  The return value keeps the reference's shape: the BEV map, or
+``(bev, aux)`` when ``is_train_height`` is set.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+
+from .view_transform import LiftSplat
+
+__all__ = ["patch_view_transform", "unpatch_view_transform"]
+
+
+def _is_bsm(backbone) -> bool:
+    return type(backbone).__name__.upper().startswith("BSM")
+
+
+def _lssfpn_single_sweep(self, sweep_index, sweep_imgs, mats_dict):
+    # lss_fpn.py:446-461, unchanged behaviour
+    batch_size, num_sweeps, num_cams, num_channels, img_height, img_width = sweep_imgs.shape
+    img_feats = self.get_cam_feats(sweep_imgs)
+    source_features = img_feats[:, 0, ...]
+    source_features = source_features.reshape(batch_size * num_cams, source_features.shape[2],
+                                              source_features.shape[3], source_features.shape[4])
+    assist_features = self.assist_layer(source_features)
+    height_feature = self._forward_height_net(source_features, mats_dict)
+    # lss_fpn.py:462-495, fused
+    feature_map = self._sgv3d_lift_splat.forward_single_sweep(height_feature, mats_dict, sweep_index)
+    if self.is_train_height:
+        return feature_map, (assist_features, assist_features)
+    return feature_map
+
+
+def _bsm_single_sweep(self, sweep_index, sweep_imgs, mats_dict):
+    # bsm_lss_fpn.py:510-522, unchanged behaviour
+    img_feats = self.get_cam_feats(sweep_imgs)
+    out = self._forward_height_net(img_feats, mats_dict)  # height, semantic1, context1, semantic0
+    # bsm_lss_fpn.py:523-559, fused
+    feature_map = self._sgv3d_lift_splat.forward_single_sweep_bsm(out[0], out[1], out[2], mats_dict, sweep_index)
+    if self.is_train_height:
+        return feature_map, (out[3], out[1])
+    return feature_map
+
+
+def patch_view_transform(backbone, arith=None, cache_plan: bool = False):
+    """Rebind ``backbone._forward_single_sweep`` to the fused path.  ``cache_plan=True`` re-uses the sorted
+    voxel-run index while the calibration tensors are unchanged (static roadside camera, inference)."""
+    for name in ("frustum", "voxel_coord", "voxel_size", "voxel_num", "output_channels"):
+        if not hasattr(backbone, name):
+            raise RuntimeError(f"{type(backbone).__name__} has no attribute {name!r}: not an LSSFPN-like module")
+    ls = LiftSplat.from_buffers(backbone.frustum, backbone.voxel_coord, backbone.voxel_size, backbone.voxel_num,
+                                backbone.output_channels, arith=arith, cache_plan=cache_plan)
+    ls = ls.to(backbone.frustum.device)
+    # plain attribute (not a registered sub-module): the state_dict of the reference module is unchanged
+    object.__setattr__(backbone, "_sgv3d_lift_splat", ls)
+    if "_forward_single_sweep" not in backbone.__dict__:
+        object.__setattr__(backbone, "_sgv3d_original_single_sweep", backbone._forward_single_sweep)
+    fn = _bsm_single_sweep if _is_bsm(backbone) else _lssfpn_single_sweep
+    object.__setattr__(backbone, "_forward_single_sweep", types.MethodType(fn, backbone))
+    return backbone
+
+
+def unpatch_view_transform(backbone):
+    if "_forward_single_sweep" in backbone.__dict__:
+        object.__delattr__(backbone, "_forward_single_sweep")
+    return backbone

@@ -324,6 +324,30 @@ class LiftSplat(nn.Module):
         self._plan_cache: Dict[tuple, LiftSplatPlan] = {}
         self._grid_const: Optional[_GridConst] = None
 
+    @classmethod
+    def from_buffers(cls, frustum, voxel_coord, voxel_size, voxel_num, output_channels: int,
+                     arith: Optional[int] = None, cache_plan: bool = False) -> "LiftSplat":
+        """Build the view transform around the four buffers an existing ``LSSFPN`` / ``BSMLSSFPN`` already
+        registered (lss_fpn.py:281-293), so that the very same fp32 values enter the kernels."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.is_bsm = False
+        self.downsample_factor = None
+        self.d_bound = None
+        self.final_dim = None
+        self.output_channels = int(output_channels)
+        self.arith = arith
+        self.cache_plan = cache_plan
+        self.register_buffer("voxel_size", voxel_size.detach().clone().float())
+        self.register_buffer("voxel_coord", voxel_coord.detach().clone().float())
+        self.register_buffer("voxel_num", voxel_num.detach().clone().long())
+        self.register_buffer("frustum", frustum.detach().clone().float())
+        self.height_channels = int(self.frustum.shape[0])
+        self._grid = tuple(int(v) for v in self.voxel_num.tolist())
+        self._plan_cache = {}
+        self._grid_const = None
+        return self
+
     def _const(self, device) -> _GridConst:
         gc = self._grid_const
         if gc is None or gc.device != device:
