@@ -51,7 +51,9 @@ struct Dims {
   int cpc;      // chunks per camera
   int nchunks;  // chunks per frame = Nc*cpc
   int V;        // X*Y voxels per frame
-  int Cpad;     // padded row length of the channels-last copies (elements)
+  int Cpad;     // padded row length of the channels-last copies (elements) = G*(4*NV + NS)
+  int G, NV, NS;  // row layout: G lanes per row, NV 4-element vectors + NS scalars per lane (transpose.cuh)
+  int Crows;    // C rounded up to 8: rows of the reduce kernel's [channel][voxel] smem tile
   int cap;      // max runs per frame (= ELL slots per frame)
   int bins2, nblk2;
   int logits;             // height tensor holds raw logits (softmax over D fused)
@@ -67,6 +69,17 @@ struct Workspace {
   size_t bytes;
 };
 
+// Row layout by channel count: the fewest load + FMA instructions per gathered row.
+void pick_row_cfg(int C, int *G, int *NV, int *NS) {
+  if (C <= 64) { *G = 16; *NV = 1; *NS = 0; }
+  else if (C <= 80) { *G = 16; *NV = 1; *NS = 1; }
+  else if (C <= 96) { *G = 16; *NV = 1; *NS = 2; }
+  else if (C <= 128) { *G = 32; *NV = 1; *NS = 0; }
+  else if (C <= 160) { *G = 32; *NV = 1; *NS = 1; }
+  else if (C <= 192) { *G = 32; *NV = 1; *NS = 2; }
+  else { *G = 32; *NV = 2; *NS = 0; }
+}
+
 Dims make_dims(const sgv3d_lift_splat_desc *d) {
   Dims m;
   m.B = d->B; m.Nc = d->Nc; m.D = d->D; m.fH = d->fH; m.fW = d->fW; m.C = d->C;
@@ -75,8 +88,9 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   m.cpc = ceil_div(m.P, kChunk);
   m.nchunks = m.Nc * m.cpc;
   m.V = m.X * m.Y;
-  const int q = d->ctx_dtype == SGV3D_DTYPE_BF16 ? 8 : 4;
-  m.Cpad = ceil_div(m.C, q) * q;
+  pick_row_cfg(m.C, &m.G, &m.NV, &m.NS);
+  m.Cpad = m.G * (4 * m.NV + m.NS);
+  m.Crows = ceil_div(m.C, 8) * 8;
   m.cap = m.nchunks * kChunk * m.D;
   m.bins2 = (m.V >> sort::kLowBits) + 1;
   m.nblk2 = ceil_div(m.cap, sort::kItemsPerBlock);
@@ -87,6 +101,8 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   m.gcs = d->grad_ctx_batch_stride ? d->grad_ctx_batch_stride : (long long)m.C * m.P;
   return m;
 }
+
+RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 16 ? 4 : 5, 4 * m.G * m.NV}; }
 
 Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   Workspace w;
@@ -109,7 +125,7 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   const size_t rows = B * m.Nc * m.P;
   if (ctx_dtype == SGV3D_DTYPE_BF16) w.ctxT = c.take<__nv_bfloat16>(rows * m.Cpad);
   else w.ctxT = c.take<float>(rows * m.Cpad);
-  const int gpad = ceil_div(m.C, 4) * 4;
+  const int gpad = m.Cpad;
   w.gT = c.take<float>(B * m.V * gpad);
   w.gctxT = c.take<float>(rows * gpad);
   w.bytes = c.used();
@@ -373,99 +389,244 @@ struct RowLoad<__nv_bfloat16> {
   }
 };
 
-constexpr int kStripV = 8;  // voxels per CTA == warps per CTA: one 32-byte sector of every channel plane
+// ---- reduce: tile geometry ----------------------------------------------------------------------
+constexpr int kTileV = 64;     // voxels per reduce CTA: two 32-voxel boxes = 2 x 128-byte rows per channel
+constexpr int kRedWarps = 8;   // warps per reduce CTA; warp w owns voxel quads w, w + 8
+constexpr int kStageE = 2048;  // entries staged in shared memory per pass
 
-// CTA = strip of 8 consecutive voxels, warp i accumulates voxel v0 + i:
-//   out[c, v] = sum_j w_j * ctx_row[pixel_j][c]   over the voxel's sorted (deterministic) entry list.
-// Entries are fetched 32 at a time with one coalesced 8-byte load per lane and broadcast from a
-// per-warp smem slot (no shuffles, no divergence bookkeeping); the inner loop is LDS.64 + LDG.128 +
-// 4 FFMA per entry with four independent row loads in flight; lanes own 4-channel slices.
-// One block barrier, then the [C][8] tile leaves as full 32-byte sectors of the NCHW planes.
-template <typename CT, int NCH>
-__global__ void __launch_bounds__(kStripV * 32)
+// Row element loads of the gather kernels: a 4-element vector / one scalar, widened to fp32.
+template <typename CT>
+struct RowLd;
+template <>
+struct RowLd<float> {
+  static __device__ __forceinline__ void vec(const float *p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ float scl(const float *p) { return __ldg(p); }
+};
+template <>
+struct RowLd<__nv_bfloat16> {
+  static __device__ __forceinline__ void vec(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ float scl(const __nv_bfloat16 *p) {
+    return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p)) << 16);
+  }
+};
+
+// acc.{x,y} = w * {x0,x1} + acc.{x,y}: one packed FFMA2 (sm_100 fma.rn.f32x2); each half rounds
+// exactly like a scalar fma.rn.
+__device__ __forceinline__ void fma2(float &a0, float &a1, float w, float x0, float x1) {
+  unsigned long long A, X, W;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(X) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(W) : "f"(w), "f"(w));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(A) : "l"(W), "l"(X), "l"(A));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
+}
+
+// Byte offset of the 16-byte chunk j (4 voxels) of channel row r inside one 32-voxel box of the
+// tile: 128-byte rows, chunk index XOR-ed with (row & 7) -- the TMA SWIZZLE_128B pattern -- so that
+// the eight lanes of a quarter-warp (rows r..r+7, same chunk) hit eight different bank groups.
+__device__ __forceinline__ int tile_chunk(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+// U batches of (32 / G) entries each: entry index j0 + (32/G)*u + sub, predicated on < hi.
+// All row loads of the batch are issued before the first FMA (U * (NV + NS) loads in flight per lane).
+template <typename CT, int G, int NV, int NS, int U, bool STAGED>
+__device__ __forceinline__ void accumulate(const CT *__restrict__ vrow, const CT *__restrict__ srow,
+                                           const Entry *__restrict__ ent, int j0, int hi, int sub,
+                                           float (&av)[NV][4], float (&as)[NS > 0 ? NS : 1]) {
+  constexpr int EPW = 32 / G;
+  Entry en[U];
+  bool ok[U];
+  float rv[U][NV][4], rs[U][NS > 0 ? NS : 1];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int idx = j0 + EPW * u + sub;
+    ok[u] = idx < hi;
+    if (ok[u]) {
+      if (STAGED) en[u] = ent[idx];
+      else {
+        const int2 t = __ldg(reinterpret_cast<const int2 *>(ent + idx));
+        en[u].off = t.x; en[u].w = __int_as_float(t.y);
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) RowLd<CT>::vec(vrow + en[u].off + 4 * k * G, rv[u][k]);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) rs[u][j] = RowLd<CT>::scl(srow + en[u].off + j * G);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (ok[u]) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        fma2(av[k][0], av[k][1], en[u].w, rv[u][k][0], rv[u][k][1]);
+        fma2(av[k][2], av[k][3], en[u].w, rv[u][k][2], rv[u][k][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) as[j] = __fmaf_rn(en[u].w, rs[u][j], as[j]);
+    }
+  }
+}
+
+// sum over the sorted entry list [lo, hi) of one voxel:  acc[c] = sum_j w_j * ctx_row[pixel_j][c]
+template <typename CT, int G, int NV, int NS, bool STAGED>
+__device__ __forceinline__ void reduce_voxel(const CT *__restrict__ vrow, const CT *__restrict__ srow,
+                                             const Entry *__restrict__ ent, int lo, int hi, int sub,
+                                             float (&av)[NV][4], float (&as)[NS > 0 ? NS : 1]) {
+  constexpr int EPW = 32 / G;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) av[k][e] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < (NS > 0 ? NS : 1); ++j) as[j] = 0.0f;
+  int j = lo;
+#pragma unroll 1
+  for (; hi - j > EPW; j += 2 * EPW) accumulate<CT, G, NV, NS, 2, STAGED>(vrow, srow, ent, j, hi, sub, av, as);
+  if (hi - j > 0) accumulate<CT, G, NV, NS, 1, STAGED>(vrow, srow, ent, j, hi, sub, av, as);
+  if (EPW == 2) {  // the two half-warps summed the even / odd entries: fixed two-term combine
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) av[k][e] = __fadd_rn(av[k][e], __shfl_xor_sync(0xffffffffu, av[k][e], 16));
+#pragma unroll
+    for (int jj = 0; jj < NS; ++jj) as[jj] = __fadd_rn(as[jj], __shfl_xor_sync(0xffffffffu, as[jj], 16));
+  }
+}
+
+// rare path (a voxel whose entry list does not fit the stage buffer): entries straight from global memory
+template <typename CT, int G, int NV, int NS>
+__device__ __noinline__ void reduce_voxel_global(const CT *__restrict__ vrow, const CT *__restrict__ srow,
+                                                 const Entry *__restrict__ ent, int lo, int hi, int sub,
+                                                 float (&av)[NV][4], float (&as)[NS > 0 ? NS : 1]) {
+  reduce_voxel<CT, G, NV, NS, false>(vrow, srow, ent, lo, hi, sub, av, as);
+}
+
+// One voxel's channel sums -> column vb (0..31) of a 32-voxel box of the swizzled [channel][voxel] tile.
+template <int G, int NV, int NS>
+__device__ __forceinline__ void store_voxel(unsigned char *box, int vb, int l, int sub, int crows,
+                                            const float (&av)[NV][4], const float (&as)[NS > 0 ? NS : 1]) {
+  if (sub != 0) return;
+  const int j = vb >> 2, o = 4 * (vb & 3);
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = l + G * (4 * k + e);
+      if (r < crows) *reinterpret_cast<float *>(box + tile_chunk(r, j) + o) = av[k][e];
+    }
+#pragma unroll
+  for (int jj = 0; jj < NS; ++jj) {
+    const int r = 4 * G * NV + jj * G + l;
+    if (r < crows) *reinterpret_cast<float *>(box + tile_chunk(r, j) + o) = as[jj];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FORWARD: per-voxel weighted gather of context rows (sparse voxel x pixel times dense pixel x C).
+// grid (ceil(V / 64), B), 256 threads.  CTA = tile of 64 consecutive voxels:
+//   1. the tile's CSR offsets and its sorted (row offset, weight) entries are staged in shared
+//      memory with coalesced loads (one round trip for the whole tile);
+//   2. warp w reduces voxel quads w and w + 8; a G-lane group owns a whole context row
+//      (NV 128-bit vectors + NS scalars per lane, 2 entries per warp instruction when G = 16),
+//      packed FFMA2, up to 8 entries in flight per warp; sums run in sorted entry order => deterministic;
+//   3. the quad's sums leave the registers as one 16-byte chunk (4 voxels) per channel into a swizzled
+//      [channel][voxel] tile (conflict-free STS.128), and the tile goes out as 128-byte row segments of the
+//      NCHW planes (fully coalesced, every output byte written exactly once).
+// ---------------------------------------------------------------------------------------------
+template <typename CT, int G, int NV, int NS>
+__global__ void __launch_bounds__(kRedWarps * 32)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
-                 const Entry *__restrict__ vm_ent, float *__restrict__ bev) {
-  extern __shared__ float tile[];            // [C][kStripV + 1]
-  __shared__ Entry s_ent[kStripV][32];
+                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *tile = smem_raw;                                     // 2 boxes x Crows x 128 B
+  Entry *s_ent = reinterpret_cast<Entry *>(smem_raw + 2 * m.Crows * 128);  // kStageE entries
+  __shared__ int s_rp[kTileV + 1];
+  constexpr int EPW = 32 / G;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int v0 = blockIdx.x * kStripV;
-  const int v = v0 + wid;
-  const int nv = min(kStripV, m.V - v0);
-  int lo = 0, hi = 0;
-  if (v < m.V) {
-    const int *rp = row_ptr + (size_t)b * (m.V + 1) + v;
-    lo = rp[0];
-    hi = rp[1];
-  }
+  const int sub = (EPW == 2) ? (lane >> 4) : 0, l = lane & (G - 1);
+  const int v0 = blockIdx.x * kTileV;
+  const int nv = min(kTileV, m.V - v0);
+  const int *rp = row_ptr + (size_t)b * (m.V + 1) + v0;
+  if (tid <= kTileV) s_rp[tid] = rp[min(tid, nv)];
+  __syncthreads();
+  const int tile_lo = s_rp[0], tile_hi = s_rp[kTileV];
   float *out = bev + (size_t)b * m.C * m.V + v0;
-  if (!__syncthreads_or(hi > lo)) {  // empty strip: zero sectors only
-    for (int i = tid; i < m.C * kStripV; i += kStripV * 32) {
-      const int c = i >> 3, j = i & 7;
-      if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, 0.0f);
+
+  if (tile_hi == tile_lo) {  // no point falls into this tile: zero fill
+    if (vec_out) {
+      for (int i = tid; i < m.C * (kTileV / 4); i += kRedWarps * 32) {
+        const int c = i / (kTileV / 4), q = i - c * (kTileV / 4);
+        if (4 * q < nv) stg_stream_f4(reinterpret_cast<float4 *>(out + (size_t)c * m.V) + q, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    } else {
+      for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
+        const int c = i / kTileV, j = i - c * kTileV;
+        if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, 0.0f);
+      }
     }
     return;
   }
-  const int nslices = m.Cpad / 4;
-  float acc[NCH][4];
-#pragma unroll
-  for (int k = 0; k < NCH; ++k)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
 
-  if (hi > lo) {
-    const CT *rows_lane = ctxT + (size_t)b * m.Nc * m.P * m.Cpad + lane * 4;  // this lane's slice 0
-    const Entry *ent = vm_ent + (size_t)b * m.cap;
-    Entry *mine = s_ent[wid];
-    for (int base = lo; base < hi; base += 32) {
-      const int cnt = min(32, hi - base);
-      __syncwarp();
-      if (lane < cnt) mine[lane] = ent[base + lane];
-      __syncwarp();
-      int q = 0;
-      for (; q + 4 <= cnt; q += 4) {
-        Entry en[4];
-        float r[4][NCH][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          en[u] = mine[q + u];  // LDS.64 broadcast
-#pragma unroll
-          for (int k = 0; k < NCH; ++k)
-            if (k * 32 + lane < nslices) RowLoad<CT>::load(rows_lane + en[u].off, k * 32, r[u][k]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int k = 0; k < NCH; ++k)
-            if (k * 32 + lane < nslices) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(en[u].w, r[u][k][e], acc[k][e]);
-            }
+  const CT *frame_rows = ctxT + (size_t)b * m.Nc * m.P * m.Cpad;
+  const CT *vrow = frame_rows + 4 * l;           // this lane's vector slice of a row
+  const CT *srow = frame_rows + 4 * G * NV + l;  // this lane's scalar of a row
+  const Entry *ent = vm_ent + (size_t)b * m.cap;
+
+  int vdone = 0, pos = tile_lo;
+  while (vdone < kTileV) {  // passes (one, unless the tile holds more than kStageE entries)
+    const int stage_hi = min(tile_hi, pos + kStageE);
+    for (int i = pos + tid; i < stage_hi; i += kRedWarps * 32) s_ent[i - pos] = ent[i];
+    int vend = kTileV;
+    if (stage_hi < tile_hi) {  // voxels whose entry lists are completely staged
+      vend = vdone;
+      while (vend < kTileV && s_rp[vend + 1] <= stage_hi) ++vend;
+    }
+    __syncthreads();
+    if (vend <= vdone) {
+      // A quad that does not fit the stage buffer: reduce it straight from global memory (one warp).
+      vend = vdone + 1;
+      if (wid == 0) {
+        const int v = vdone;
+        float av[NV][4], as[NS > 0 ? NS : 1];
+        reduce_voxel_global<CT, G, NV, NS>(vrow, srow, ent, s_rp[v], s_rp[v + 1], sub, av, as);
+        store_voxel<G, NV, NS>(tile + (v >> 5) * m.Crows * 128, v & 31, l, sub, m.Crows, av, as);
       }
-      for (; q < cnt; ++q) {
-        const Entry en = mine[q];
-#pragma unroll
-        for (int k = 0; k < NCH; ++k)
-          if (k * 32 + lane < nslices) {
-            float r1[4];
-            RowLoad<CT>::load(rows_lane + en.off, k * 32, r1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[k][e] = __fmaf_rn(en.w, r1[e], acc[k][e]);
-          }
+    } else {
+      const Entry *staged = s_ent - pos;
+      for (int v = vdone + wid; v < vend; v += kRedWarps) {
+        float av[NV][4], as[NS > 0 ? NS : 1];
+        reduce_voxel<CT, G, NV, NS, true>(vrow, srow, staged, s_rp[v], s_rp[v + 1], sub, av, as);
+        store_voxel<G, NV, NS>(tile + (v >> 5) * m.Crows * 128, v & 31, l, sub, m.Crows, av, as);
       }
     }
+    __syncthreads();
+    vdone = vend;
+    pos = s_rp[vend];
   }
-#pragma unroll
-  for (int k = 0; k < NCH; ++k)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = (k * 32 + lane) * 4 + e;
-      if (c < m.C) tile[c * (kStripV + 1) + wid] = acc[k][e];
+
+  // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line
+  if (vec_out) {
+    for (int i = tid; i < m.C * (kTileV / 4); i += kRedWarps * 32) {
+      const int c = i >> 4, q = i & 15;
+      if (4 * q < nv) {
+        const float4 t = *reinterpret_cast<const float4 *>(tile + (q >> 3) * m.Crows * 128 + tile_chunk(c, q & 7));
+        stg_stream_f4(reinterpret_cast<float4 *>(out + (size_t)c * m.V) + q, t);
+      }
     }
-  __syncthreads();
-  for (int i = tid; i < m.C * kStripV; i += kStripV * 32) {
-    const int c = i >> 3, j = i & 7;
-    if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, tile[c * (kStripV + 1) + j]);
+  } else {
+    for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
+      const int c = i >> 6, j = i & 63, q = j >> 2;
+      if (j < nv)
+        stg_stream_f1(out + (size_t)c * m.V + j,
+                      *reinterpret_cast<const float *>(tile + (q >> 3) * m.Crows * 128 + tile_chunk(c, q & 7) + 4 * (j & 3)));
+    }
   }
 }
 
@@ -660,17 +821,30 @@ int set_smem(K kernel, size_t bytes) {
   return SGV3D_OK;
 }
 
-template <typename CT>
-int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
-  dim3 grid(ceil_div(m.V, kStripV), m.B);
-  const size_t smem = sizeof(float) * m.C * (kStripV + 1);
-  const CT *ctxT = static_cast<const CT *>(w.ctxT);
-  if (m.Cpad <= 128)
-    ls_reduce_kernel<CT, 1><<<grid, kStripV * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_ent, bev);
-  else
-    ls_reduce_kernel<CT, 2><<<grid, kStripV * 32, smem, s>>>(m, ctxT, w.row_ptr, w.vm_ent, bev);
+template <typename CT, int G, int NV, int NS>
+int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+  dim3 grid(ceil_div(m.V, kTileV), m.B);
+  const size_t smem = (size_t)2 * m.Crows * 128 + sizeof(Entry) * kStageE;
+  if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NS>, smem)) return rc;
+  // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
+  const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
+  ls_reduce_kernel<CT, G, NV, NS><<<grid, kRedWarps * 32, smem, s>>>(
+      m, static_cast<const CT *>(w.ctxT), w.row_ptr, w.vm_ent, bev, vec_out);
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
+}
+
+template <typename CT>
+int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+  if (m.G == 16) {
+    if (m.NS == 0) return launch_reduce_cfg<CT, 16, 1, 0>(m, w, bev, s);
+    if (m.NS == 1) return launch_reduce_cfg<CT, 16, 1, 1>(m, w, bev, s);
+    return launch_reduce_cfg<CT, 16, 1, 2>(m, w, bev, s);
+  }
+  if (m.NV == 2) return launch_reduce_cfg<CT, 32, 2, 0>(m, w, bev, s);
+  if (m.NS == 0) return launch_reduce_cfg<CT, 32, 1, 0>(m, w, bev, s);
+  if (m.NS == 1) return launch_reduce_cfg<CT, 32, 1, 1>(m, w, bev, s);
+  return launch_reduce_cfg<CT, 32, 1, 2>(m, w, bev, s);
 }
 
 template <typename CT>
@@ -691,13 +865,13 @@ int transpose_context(const Dims &m, const Workspace &w, int ctx_dtype, const vo
                       cudaStream_t s) {
   const int batch = m.B * m.Nc;
   if (ctx_dtype == SGV3D_DTYPE_BF16)
-    launch_transpose_pad<__nv_bfloat16, __nv_bfloat16>(
+    launch_transpose_pad<__nv_bfloat16, __nv_bfloat16, 1>(
         static_cast<const __nv_bfloat16 *>(context), static_cast<__nv_bfloat16 *>(w.ctxT), batch, m.C,
-        m.P, m.P, (size_t)m.cs, m.Cpad, (size_t)m.P * m.Cpad, s);
+        m.P, m.P, (size_t)m.cs, m.Cpad, (size_t)m.P * m.Cpad, s, row_perm(m));
   else
-    launch_transpose_pad<float, float>(static_cast<const float *>(context), static_cast<float *>(w.ctxT),
-                                       batch, m.C, m.P, m.P, (size_t)m.cs, m.Cpad,
-                                       (size_t)m.P * m.Cpad, s);
+    launch_transpose_pad<float, float, 1>(static_cast<const float *>(context), static_cast<float *>(w.ctxT),
+                                          batch, m.C, m.P, m.P, (size_t)m.cs, m.Cpad,
+                                          (size_t)m.P * m.Cpad, s, row_perm(m));
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(context)");
   return SGV3D_OK;
 }
@@ -817,10 +991,10 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_backward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
-  const int gpad = ceil_div(m.C, 4) * 4;
+  const int gpad = m.Cpad;  // gradient rows share the context rows' (permuted) channel layout
   if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
-  launch_transpose_pad<float, float>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
-                                     (size_t)m.V * gpad, s);
+  launch_transpose_pad<float, float, 1>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
+                                        (size_t)m.V * gpad, s, row_perm(m));
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_bev)");
   if (int rc = launch_weights<false>(m, w, height, s)) return rc;
   int rc = desc->ctx_dtype == SGV3D_DTYPE_BF16 ? launch_backward_gather<__nv_bfloat16>(m, w, gpad, s)
@@ -837,8 +1011,8 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
                                               grad_height, nullptr);
   }
   SGV3D_CHECK_LAUNCH("ls_expand_kernel");
-  launch_transpose_pad<float, float>(w.gctxT, grad_context, m.B * m.Nc, m.P, m.C, gpad,
-                                     (size_t)m.P * gpad, m.P, (size_t)m.gcs, s);
+  launch_transpose_pad<float, float, 2>(w.gctxT, grad_context, m.B * m.Nc, m.P, m.C, gpad,
+                                        (size_t)m.P * gpad, m.P, (size_t)m.gcs, s, row_perm(m));
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_context)");
   return SGV3D_OK;
 }
