@@ -38,10 +38,11 @@ namespace {
 
 constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
 
-// Sorted (voxel-major) entry: element offset of the pixel's context row inside the frame's
-// channels-last copy (written by the plan), and the run weight (written by the forward weights pass).
+// Sorted (voxel-major) entry: BYTE offset of the pixel's context row inside the frame's channels-last
+// copy (a multiple of 64) OR-ed with the voxel's index inside its 64-voxel reduce tile (written by the
+// plan), and the run weight (written by the forward weights pass).
 struct __align__(8) Entry {
-  int off;
+  unsigned off;
   float w;
 };
 
@@ -52,8 +53,8 @@ struct Dims {
   int nchunks;  // chunks per frame = Nc*cpc
   int V;        // X*Y voxels per frame
   int Cpad;     // padded row length of the channels-last copies (elements) = G*(4*NV + NS)
-  int G, NV, NS;  // row layout: G lanes per row, NV 4-element vectors + NS scalars per lane (transpose.cuh)
-  int Crows;    // C rounded up to 8: rows of the reduce kernel's [channel][voxel] smem tile
+  int G, NV;    // row layout: G lanes per row, NV 4-element vectors per lane (transpose.cuh)
+  int esize;    // bytes per context element (4 fp32, 2 bf16)
   int cap;      // max runs per frame (= ELL slots per frame)
   int bins2, nblk2;
   int logits;             // height tensor holds raw logits (softmax over D fused)
@@ -69,15 +70,11 @@ struct Workspace {
   size_t bytes;
 };
 
-// Row layout by channel count: the fewest load + FMA instructions per gathered row.
-void pick_row_cfg(int C, int *G, int *NV, int *NS) {
-  if (C <= 64) { *G = 16; *NV = 1; *NS = 0; }
-  else if (C <= 80) { *G = 16; *NV = 1; *NS = 1; }
-  else if (C <= 96) { *G = 16; *NV = 1; *NS = 2; }
-  else if (C <= 128) { *G = 32; *NV = 1; *NS = 0; }
-  else if (C <= 160) { *G = 32; *NV = 1; *NS = 1; }
-  else if (C <= 192) { *G = 32; *NV = 1; *NS = 2; }
-  else { *G = 32; *NV = 2; *NS = 0; }
+// Row layout by channel count: a G-lane group owns a whole channels-last row, NV 4-element vectors per
+// lane (Cpad = 4*G*NV, a multiple of 32 elements so that no 128-byte group access straddles a line).
+void pick_row_cfg(int C, int *G, int *NV) {
+  if (C <= 128) { *G = 8; *NV = ceil_div(C, 32); }
+  else { *G = 16; *NV = ceil_div(C, 64); }
 }
 
 Dims make_dims(const sgv3d_lift_splat_desc *d) {
@@ -88,9 +85,9 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   m.cpc = ceil_div(m.P, kChunk);
   m.nchunks = m.Nc * m.cpc;
   m.V = m.X * m.Y;
-  pick_row_cfg(m.C, &m.G, &m.NV, &m.NS);
-  m.Cpad = m.G * (4 * m.NV + m.NS);
-  m.Crows = ceil_div(m.C, 8) * 8;
+  pick_row_cfg(m.C, &m.G, &m.NV);
+  m.Cpad = 4 * m.G * m.NV;
+  m.esize = d->ctx_dtype == SGV3D_DTYPE_BF16 ? 2 : 4;
   m.cap = m.nchunks * kChunk * m.D;
   m.bins2 = (m.V >> sort::kLowBits) + 1;
   m.nblk2 = ceil_div(m.cap, sort::kItemsPerBlock);
@@ -102,7 +99,7 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   return m;
 }
 
-RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 16 ? 4 : 5, 4 * m.G * m.NV}; }
+RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 8 ? 3 : 4, m.Cpad}; }
 
 Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   Workspace w;
@@ -245,24 +242,24 @@ struct PlanPlace {
   int *keys2;
   Entry *vm_ent;
   int *run_dst;
-  int D, cpc, P, Cpad;
+  int D, cpc, P, row_bytes;
   __device__ __forceinline__ void operator()(int pos, int key, int slot) const {
     keys2[pos] = key;
     run_dst[slot] = pos;
     const int t = slot & (kChunk - 1);
     const int chunk = (slot / kChunk) / D;
     const int n = chunk / cpc, ci = chunk - n * cpc;
-    vm_ent[pos].off = (n * P + ci * kChunk + t) * Cpad;
+    vm_ent[pos].off = (unsigned)(n * P + ci * kChunk + t) * (unsigned)row_bytes | (unsigned)(key & 63);
   }
 };
 struct PlanPlaceFactory {
   int *keys2;
   Entry *vm_ent;
   int *run_dst;
-  int D, cpc, P, Cpad, cap;
+  int D, cpc, P, row_bytes, cap;
   __device__ __forceinline__ PlanPlace operator()(int frame) const {
     const size_t o = (size_t)frame * cap;
-    return PlanPlace{keys2 + o, vm_ent + o, run_dst + o, D, cpc, P, Cpad};
+    return PlanPlace{keys2 + o, vm_ent + o, run_dst + o, D, cpc, P, row_bytes};
   }
 };
 
@@ -391,33 +388,30 @@ struct RowLoad<__nv_bfloat16> {
 
 // ---- reduce: tile geometry ----------------------------------------------------------------------
 constexpr int kTileV = 64;     // voxels per reduce CTA: two 32-voxel boxes = 2 x 128-byte rows per channel
-constexpr int kRedWarps = 8;   // warps per reduce CTA; warp w owns voxel quads w, w + 8
-constexpr int kStageE = 2048;  // entries staged in shared memory per pass
+constexpr int kRedWarps = 8;   // warps per reduce CTA
+constexpr int kStageE = 2048;  // entries staged in shared memory (larger tiles read them from global)
+static_assert(kTileV == 64, "Entry::off carries the voxel-in-tile index in its low 6 bits");
 
-// Row element loads of the gather kernels: a 4-element vector / one scalar, widened to fp32.
+// 4-element row vector widened to fp32 (byte address).
 template <typename CT>
 struct RowLd;
 template <>
 struct RowLd<float> {
-  static __device__ __forceinline__ void vec(const float *p, float (&v)[4]) {
+  static __device__ __forceinline__ void vec(const unsigned char *p, float (&v)[4]) {
     const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
-  static __device__ __forceinline__ float scl(const float *p) { return __ldg(p); }
 };
 template <>
 struct RowLd<__nv_bfloat16> {
-  static __device__ __forceinline__ void vec(const __nv_bfloat16 *p, float (&v)[4]) {
+  static __device__ __forceinline__ void vec(const unsigned char *p, float (&v)[4]) {
     const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
     v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
     v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
   }
-  static __device__ __forceinline__ float scl(const __nv_bfloat16 *p) {
-    return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p)) << 16);
-  }
 };
 
-// acc.{x,y} = w * {x0,x1} + acc.{x,y}: one packed FFMA2 (sm_100 fma.rn.f32x2); each half rounds
+// acc.{0,1} = w * {x0,x1} + acc.{0,1}: one packed FFMA2 (sm_100 fma.rn.f32x2); each half rounds
 // exactly like a scalar fma.rn.
 __device__ __forceinline__ void fma2(float &a0, float &a1, float w, float x0, float x1) {
   unsigned long long A, X, W;
@@ -427,130 +421,113 @@ __device__ __forceinline__ void fma2(float &a0, float &a1, float w, float x0, fl
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(A) : "l"(W), "l"(X), "l"(A));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
 }
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 
 // Byte offset of the 16-byte chunk j (4 voxels) of channel row r inside one 32-voxel box of the
 // tile: 128-byte rows, chunk index XOR-ed with (row & 7) -- the TMA SWIZZLE_128B pattern -- so that
-// the eight lanes of a quarter-warp (rows r..r+7, same chunk) hit eight different bank groups.
+// lanes holding rows r, r+1, .. r+7 of the same voxel column hit eight different bank groups.
 __device__ __forceinline__ int tile_chunk(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
-// U batches of (32 / G) entries each: entry index j0 + (32/G)*u + sub, predicated on < hi.
-// All row loads of the batch are issued before the first FMA (U * (NV + NS) loads in flight per lane).
-template <typename CT, int G, int NV, int NS, int U, bool STAGED>
-__device__ __forceinline__ void accumulate(const CT *__restrict__ vrow, const CT *__restrict__ srow,
-                                           const Entry *__restrict__ ent, int j0, int hi, int sub,
-                                           float (&av)[NV][4], float (&as)[NS > 0 ? NS : 1]) {
-  constexpr int EPW = 32 / G;
-  Entry en[U];
-  bool ok[U];
-  float rv[U][NV][4], rs[U][NS > 0 ? NS : 1];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int idx = j0 + EPW * u + sub;
-    ok[u] = idx < hi;
-    if (ok[u]) {
-      if (STAGED) en[u] = ent[idx];
-      else {
-        const int2 t = __ldg(reinterpret_cast<const int2 *>(ent + idx));
-        en[u].off = t.x; en[u].w = __int_as_float(t.y);
-      }
-#pragma unroll
-      for (int k = 0; k < NV; ++k) RowLd<CT>::vec(vrow + en[u].off + 4 * k * G, rv[u][k]);
-#pragma unroll
-      for (int j = 0; j < NS; ++j) rs[u][j] = RowLd<CT>::scl(srow + en[u].off + j * G);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (ok[u]) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        fma2(av[k][0], av[k][1], en[u].w, rv[u][k][0], rv[u][k][1]);
-        fma2(av[k][2], av[k][3], en[u].w, rv[u][k][2], rv[u][k][3]);
-      }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) as[j] = __fmaf_rn(en[u].w, rs[u][j], as[j]);
-    }
-  }
-}
-
-// sum over the sorted entry list [lo, hi) of one voxel:  acc[c] = sum_j w_j * ctx_row[pixel_j][c]
-template <typename CT, int G, int NV, int NS, bool STAGED>
-__device__ __forceinline__ void reduce_voxel(const CT *__restrict__ vrow, const CT *__restrict__ srow,
-                                             const Entry *__restrict__ ent, int lo, int hi, int sub,
-                                             float (&av)[NV][4], float (&as)[NS > 0 ? NS : 1]) {
-  constexpr int EPW = 32 / G;
+// One stream = one G-lane group walking a contiguous slice [j, jend) of the tile's sorted entries.
+// Lane l owns channels l + G*t (t < 4*NV) of every gathered row; a voxel's sum is complete when the
+// voxel index carried by the entries changes, and is then written to column vt of the tile.
+template <typename CT, int G, int NV, bool STAGED>
+__device__ __forceinline__ void run_stream(const unsigned char *__restrict__ lane_rows,
+                                           const Entry *__restrict__ ent, int j, int jend,
+                                           unsigned tile_lane /*smem addr of row l, chunk 0*/, int l7,
+                                           unsigned box_bytes) {
+  float acc[NV][4];
 #pragma unroll
   for (int k = 0; k < NV; ++k)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) av[k][e] = 0.0f;
-#pragma unroll
-  for (int j = 0; j < (NS > 0 ? NS : 1); ++j) as[j] = 0.0f;
-  int j = lo;
-#pragma unroll 1
-  for (; hi - j > EPW; j += 2 * EPW) accumulate<CT, G, NV, NS, 2, STAGED>(vrow, srow, ent, j, hi, sub, av, as);
-  if (hi - j > 0) accumulate<CT, G, NV, NS, 1, STAGED>(vrow, srow, ent, j, hi, sub, av, as);
-  if (EPW == 2) {  // the two half-warps summed the even / odd entries: fixed two-term combine
+    for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
+  int cur = -1;
+  auto flush = [&]() {
+    const unsigned a = tile_lane + (cur >> 5) * box_bytes + (((((unsigned)cur >> 2) & 7u) ^ (unsigned)l7) << 4) +
+                       (((unsigned)cur & 3u) << 2);
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) av[k][e] = __fadd_rn(av[k][e], __shfl_xor_sync(0xffffffffu, av[k][e], 16));
+      for (int e = 0; e < 4; ++e) {
+        sts_f32(a + (4 * k + e) * G * 128, acc[k][e]);
+        acc[k][e] = 0.0f;
+      }
+  };
+  constexpr int U = 2;
+  // the groups of a warp iterate in lockstep: uniform trip count = the longest slice
+  const int len = jend - j;
+  int iters = (len + U - 1) / U;
 #pragma unroll
-    for (int jj = 0; jj < NS; ++jj) as[jj] = __fadd_rn(as[jj], __shfl_xor_sync(0xffffffffu, as[jj], 16));
-  }
-}
-
-// rare path (a voxel whose entry list does not fit the stage buffer): entries straight from global memory
-template <typename CT, int G, int NV, int NS>
-__device__ __noinline__ void reduce_voxel_global(const CT *__restrict__ vrow, const CT *__restrict__ srow,
-                                                 const Entry *__restrict__ ent, int lo, int hi, int sub,
-                                                 float (&av)[NV][4], float (&as)[NS > 0 ? NS : 1]) {
-  reduce_voxel<CT, G, NV, NS, false>(vrow, srow, ent, lo, hi, sub, av, as);
-}
-
-// One voxel's channel sums -> column vb (0..31) of a 32-voxel box of the swizzled [channel][voxel] tile.
-template <int G, int NV, int NS>
-__device__ __forceinline__ void store_voxel(unsigned char *box, int vb, int l, int sub, int crows,
-                                            const float (&av)[NV][4], const float (&as)[NS > 0 ? NS : 1]) {
-  if (sub != 0) return;
-  const int j = vb >> 2, o = 4 * (vb & 3);
+  for (int o = G; o < 32; o <<= 1) iters = max(iters, __shfl_xor_sync(0xffffffffu, iters, o));
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it, j += U) {
+    Entry en[U];
+    bool ok[U];
+    float r[U][NV][4];
 #pragma unroll
-  for (int k = 0; k < NV; ++k)
+    for (int u = 0; u < U; ++u) {
+      ok[u] = j + u < jend;
+      if (ok[u]) {
+        if (STAGED) en[u] = ent[j + u];
+        else {
+          const uint2 t = __ldg(reinterpret_cast<const uint2 *>(ent + j + u));
+          en[u].off = t.x; en[u].w = __uint_as_float(t.y);
+        }
+        const unsigned char *row = lane_rows + (en[u].off & ~63u);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = l + G * (4 * k + e);
-      if (r < crows) *reinterpret_cast<float *>(box + tile_chunk(r, j) + o) = av[k][e];
+        for (int k = 0; k < NV; ++k) RowLd<CT>::vec(row + k * G * 4 * sizeof(CT), r[u][k]);
+      }
     }
 #pragma unroll
-  for (int jj = 0; jj < NS; ++jj) {
-    const int r = 4 * G * NV + jj * G + l;
-    if (r < crows) *reinterpret_cast<float *>(box + tile_chunk(r, j) + o) = as[jj];
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) {
+        const int vt = (int)(en[u].off & 63u);
+        if (vt != cur) {
+          if (cur >= 0) flush();
+          cur = vt;
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          fma2(acc[k][0], acc[k][1], en[u].w, r[u][k][0], r[u][k][1]);
+          fma2(acc[k][2], acc[k][3], en[u].w, r[u][k][2], r[u][k][3]);
+        }
+      }
+    }
   }
+  if (cur >= 0) flush();
 }
 
 // ---------------------------------------------------------------------------------------------
 // FORWARD: per-voxel weighted gather of context rows (sparse voxel x pixel times dense pixel x C).
 // grid (ceil(V / 64), B), 256 threads.  CTA = tile of 64 consecutive voxels:
-//   1. the tile's CSR offsets and its sorted (row offset, weight) entries are staged in shared
-//      memory with coalesced loads (one round trip for the whole tile);
-//   2. warp w reduces voxel quads w and w + 8; a G-lane group owns a whole context row
-//      (NV 128-bit vectors + NS scalars per lane, 2 entries per warp instruction when G = 16),
-//      packed FFMA2, up to 8 entries in flight per warp; sums run in sorted entry order => deterministic;
-//   3. the quad's sums leave the registers as one 16-byte chunk (4 voxels) per channel into a swizzled
-//      [channel][voxel] tile (conflict-free STS.128), and the tile goes out as 128-byte row segments of the
-//      NCHW planes (fully coalesced, every output byte written exactly once).
+//   1. the tile's CSR offsets and its sorted (row offset | voxel, weight) entries are staged in shared
+//      memory with coalesced loads (one round trip for the whole tile); the [channel][voxel] tile is zeroed;
+//   2. the tile's entry list is cut at voxel boundaries into 32 (G = 8) or 16 (G = 16) slices of near-equal
+//      length, one per G-lane group ("stream"): perfectly regular work whatever the points-per-voxel
+//      distribution looks like.  A group owns whole context rows (NV 128-bit loads per lane and entry, 4
+//      entries per warp instruction when G = 8), packed FFMA2, 2 entries per stream in flight; every
+//      voxel is summed by exactly one stream in sorted entry order => deterministic, no atomics;
+//   3. finished voxel sums go to a swizzled [channel][voxel] tile (conflict-free for G = 8), and the
+//      tile leaves as 128-byte row segments of the NCHW planes (fully coalesced, every output byte
+//      written exactly once).
 // ---------------------------------------------------------------------------------------------
-template <typename CT, int G, int NV, int NS>
+template <typename CT, int G, int NV>
 __global__ void __launch_bounds__(kRedWarps * 32)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
                  const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char *tile = smem_raw;                                     // 2 boxes x Crows x 128 B
-  Entry *s_ent = reinterpret_cast<Entry *>(smem_raw + 2 * m.Crows * 128);  // kStageE entries
+  constexpr int kRows = 4 * G * NV;                  // = Cpad rows (rows >= C are scratch)
+  constexpr unsigned kBoxBytes = kRows * 128;
+  unsigned char *tile = smem_raw;                                       // 2 boxes x kRows x 128 B
+  Entry *s_ent = reinterpret_cast<Entry *>(smem_raw + 2 * kBoxBytes);   // kStageE entries
   __shared__ int s_rp[kTileV + 1];
-  constexpr int EPW = 32 / G;
+  constexpr int SPW = 32 / G;              // streams per warp
+  constexpr int NSTR = kRedWarps * SPW;    // streams per CTA
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int sub = (EPW == 2) ? (lane >> 4) : 0, l = lane & (G - 1);
+  const int sub = lane / G, l = lane & (G - 1);
   const int v0 = blockIdx.x * kTileV;
   const int nv = min(kTileV, m.V - v0);
   const int *rp = row_ptr + (size_t)b * (m.V + 1) + v0;
@@ -562,61 +539,59 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   if (tile_hi == tile_lo) {  // no point falls into this tile: zero fill
     if (vec_out) {
       for (int i = tid; i < m.C * (kTileV / 4); i += kRedWarps * 32) {
-        const int c = i / (kTileV / 4), q = i - c * (kTileV / 4);
+        const int c = i >> 4, q = i & 15;
         if (4 * q < nv) stg_stream_f4(reinterpret_cast<float4 *>(out + (size_t)c * m.V) + q, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     } else {
       for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
-        const int c = i / kTileV, j = i - c * kTileV;
+        const int c = i >> 6, j = i & 63;
         if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, 0.0f);
       }
     }
     return;
   }
 
-  const CT *frame_rows = ctxT + (size_t)b * m.Nc * m.P * m.Cpad;
-  const CT *vrow = frame_rows + 4 * l;           // this lane's vector slice of a row
-  const CT *srow = frame_rows + 4 * G * NV + l;  // this lane's scalar of a row
+  const int n_t = tile_hi - tile_lo;
+  const bool staged = n_t <= kStageE;
   const Entry *ent = vm_ent + (size_t)b * m.cap;
+  if (staged)
+    for (int i = tid; i < n_t; i += kRedWarps * 32) s_ent[i] = ent[tile_lo + i];
+  for (int i = tid; i < 2 * (int)kBoxBytes / 16; i += kRedWarps * 32)
+    reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  int vdone = 0, pos = tile_lo;
-  while (vdone < kTileV) {  // passes (one, unless the tile holds more than kStageE entries)
-    const int stage_hi = min(tile_hi, pos + kStageE);
-    for (int i = pos + tid; i < stage_hi; i += kRedWarps * 32) s_ent[i - pos] = ent[i];
-    int vend = kTileV;
-    if (stage_hi < tile_hi) {  // voxels whose entry lists are completely staged
-      vend = vdone;
-      while (vend < kTileV && s_rp[vend + 1] <= stage_hi) ++vend;
-    }
-    __syncthreads();
-    if (vend <= vdone) {
-      // A quad that does not fit the stage buffer: reduce it straight from global memory (one warp).
-      vend = vdone + 1;
-      if (wid == 0) {
-        const int v = vdone;
-        float av[NV][4], as[NS > 0 ? NS : 1];
-        reduce_voxel_global<CT, G, NV, NS>(vrow, srow, ent, s_rp[v], s_rp[v + 1], sub, av, as);
-        store_voxel<G, NV, NS>(tile + (v >> 5) * m.Crows * 128, v & 31, l, sub, m.Crows, av, as);
-      }
-    } else {
-      const Entry *staged = s_ent - pos;
-      for (int v = vdone + wid; v < vend; v += kRedWarps) {
-        float av[NV][4], as[NS > 0 ? NS : 1];
-        reduce_voxel<CT, G, NV, NS, true>(vrow, srow, staged, s_rp[v], s_rp[v + 1], sub, av, as);
-        store_voxel<G, NV, NS>(tile + (v >> 5) * m.Crows * 128, v & 31, l, sub, m.Crows, av, as);
-      }
-    }
-    __syncthreads();
-    vdone = vend;
-    pos = s_rp[vend];
+  // stream s owns the voxels [vb(s), vb(s+1)),  vb(k) = #{v in [0, 64] : rp[v] < tile_lo + k * n_t / NSTR}
+  // (rp is non-decreasing; vb(0) = 0, vb(NSTR) = 64): slices of near-equal entry counts cut at voxel
+  // boundaries.  Counted with two ballots over the 65 offsets held one / two per lane.
+  const int rp_a = s_rp[lane], rp_b = s_rp[32 + lane];
+  int vs = 0, ve = 0;
+#pragma unroll
+  for (int ss = 0; ss <= SPW; ++ss) {
+    const int k = wid * SPW + ss;
+    const int target = tile_lo + (int)(((long long)n_t * k) / NSTR);
+    const int vb = __popc(__ballot_sync(0xffffffffu, rp_a < target)) + __popc(__ballot_sync(0xffffffffu, rp_b < target));
+    if (ss == sub) vs = vb;
+    if (ss == sub + 1) ve = vb;
   }
+  int jb[2];
+  jb[0] = s_rp[vs];
+  jb[1] = s_rp[ve];
+  __syncthreads();
+
+  const unsigned char *lane_rows = reinterpret_cast<const unsigned char *>(ctxT) +
+                                   ((size_t)b * m.Nc * m.P * m.Cpad + 4 * l) * sizeof(CT);
+  const unsigned tile_lane = (unsigned)__cvta_generic_to_shared(tile) + l * 128;
+  if (staged)
+    run_stream<CT, G, NV, true>(lane_rows, s_ent - tile_lo, jb[0], jb[1], tile_lane, l & 7, kBoxBytes);
+  else
+    run_stream<CT, G, NV, false>(lane_rows, ent, jb[0], jb[1], tile_lane, l & 7, kBoxBytes);
+  __syncthreads();
 
   // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line
   if (vec_out) {
     for (int i = tid; i < m.C * (kTileV / 4); i += kRedWarps * 32) {
       const int c = i >> 4, q = i & 15;
       if (4 * q < nv) {
-        const float4 t = *reinterpret_cast<const float4 *>(tile + (q >> 3) * m.Crows * 128 + tile_chunk(c, q & 7));
+        const float4 t = *reinterpret_cast<const float4 *>(tile + (q >> 3) * kBoxBytes + tile_chunk(c, q & 7));
         stg_stream_f4(reinterpret_cast<float4 *>(out + (size_t)c * m.V) + q, t);
       }
     }
@@ -625,7 +600,7 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
       const int c = i >> 6, j = i & 63, q = j >> 2;
       if (j < nv)
         stg_stream_f1(out + (size_t)c * m.V + j,
-                      *reinterpret_cast<const float *>(tile + (q >> 3) * m.Crows * 128 + tile_chunk(c, q & 7) + 4 * (j & 3)));
+                      *reinterpret_cast<const float *>(tile + (q >> 3) * kBoxBytes + tile_chunk(c, q & 7) + 4 * (j & 3)));
     }
   }
 }
@@ -821,14 +796,14 @@ int set_smem(K kernel, size_t bytes) {
   return SGV3D_OK;
 }
 
-template <typename CT, int G, int NV, int NS>
+template <typename CT, int G, int NV>
 int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
   dim3 grid(ceil_div(m.V, kTileV), m.B);
-  const size_t smem = (size_t)2 * m.Crows * 128 + sizeof(Entry) * kStageE;
-  if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NS>, smem)) return rc;
+  const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(Entry) * kStageE;
+  if (int rc = set_smem(ls_reduce_kernel<CT, G, NV>, smem)) return rc;
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
-  ls_reduce_kernel<CT, G, NV, NS><<<grid, kRedWarps * 32, smem, s>>>(
+  ls_reduce_kernel<CT, G, NV><<<grid, kRedWarps * 32, smem, s>>>(
       m, static_cast<const CT *>(w.ctxT), w.row_ptr, w.vm_ent, bev, vec_out);
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
@@ -836,15 +811,16 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
 
 template <typename CT>
 int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
-  if (m.G == 16) {
-    if (m.NS == 0) return launch_reduce_cfg<CT, 16, 1, 0>(m, w, bev, s);
-    if (m.NS == 1) return launch_reduce_cfg<CT, 16, 1, 1>(m, w, bev, s);
-    return launch_reduce_cfg<CT, 16, 1, 2>(m, w, bev, s);
+  if (m.G == 8) {
+    switch (m.NV) {
+      case 1: return launch_reduce_cfg<CT, 8, 1>(m, w, bev, s);
+      case 2: return launch_reduce_cfg<CT, 8, 2>(m, w, bev, s);
+      case 3: return launch_reduce_cfg<CT, 8, 3>(m, w, bev, s);
+      default: return launch_reduce_cfg<CT, 8, 4>(m, w, bev, s);
+    }
   }
-  if (m.NV == 2) return launch_reduce_cfg<CT, 32, 2, 0>(m, w, bev, s);
-  if (m.NS == 0) return launch_reduce_cfg<CT, 32, 1, 0>(m, w, bev, s);
-  if (m.NS == 1) return launch_reduce_cfg<CT, 32, 1, 1>(m, w, bev, s);
-  return launch_reduce_cfg<CT, 32, 1, 2>(m, w, bev, s);
+  if (m.NV <= 3) return launch_reduce_cfg<CT, 16, 3>(m, w, bev, s);
+  return launch_reduce_cfg<CT, 16, 4>(m, w, bev, s);
 }
 
 template <typename CT>
@@ -953,7 +929,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF, PlanPlaceFactory>
       <<<g2, sort::kThreads, sizeof(int) * sort::kWarps * m.bins2, s>>>(
           w.keys1, w.pay1, (size_t)m.cap, w.count, 0, m.bins2, w.hist2, m.nblk2,
-          PlanPlaceFactory{w.keys2, w.vm_ent, w.run_dst, m.D, m.cpc, m.P, m.Cpad, m.cap});
+          PlanPlaceFactory{w.keys2, w.vm_ent, w.run_dst, m.D, m.cpc, m.P, m.Cpad * m.esize, m.cap});
   SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
   const int gxr = ceil_div(m.cap, 256) < 128 ? ceil_div(m.cap, 256) : 128;
   sort::row_ptr_kernel<<<dim3(gxr, m.B), 256, 0, s>>>(w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr);
