@@ -63,7 +63,7 @@ struct Dims {
 };
 
 struct Workspace {
-  int *count, *run_cnt, *run_vox, *run_d, *run_dst, *hist1, *keys1, *pay1, *hist2, *keys2, *row_ptr;
+  int *count, *run_cnt, *run_vox, *run_d, *run_dst, *hist1, *keys1, *pay1, *hist2, *keys2, *row_ptr, *chunk_done;
   Entry *vm_ent;  // sorted (row offset, weight) pairs
   float *w_pm, *gw_pm, *gT, *gctxT;
   void *ctxT;
@@ -106,6 +106,7 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   Carver c(ws);
   const size_t B = m.B, slots = (size_t)m.B * m.cap;
   w.count = c.take<int>(B);
+  w.chunk_done = c.take<int>(B * m.nchunks);
   w.run_cnt = c.take<int>(B * m.nchunks * kChunk);
   w.run_vox = c.take<int>(slots);
   w.run_d = c.take<int>(slots);
@@ -144,11 +145,12 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
                     const float *__restrict__ mv, const float *__restrict__ me,
                     const float *__restrict__ bda, const float *__restrict__ ref_h, geom::Grid grid,
                     int *__restrict__ run_cnt, int *__restrict__ run_vox, int *__restrict__ run_d,
-                    int *__restrict__ hist1) {
+                    int *__restrict__ hist1, const int *__restrict__ chunk_done) {
   __shared__ geom::Camera cam;
   __shared__ int s_hist[sort::kLowBins];
   extern __shared__ float z_s[];
   const int b = blockIdx.y, chunk = blockIdx.x;
+  if (chunk_done[b * m.nchunks + chunk]) return;  // the fast kernel already produced this chunk
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int bn = b * m.Nc + n;
   const int t = threadIdx.x;
@@ -192,6 +194,95 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
   }
   run_cnt[(size_t)frame_chunk * kChunk + t] = r;
   __syncthreads();
+  int *hh = hist1 + (size_t)b * sort::kLowBins * m.nchunks;
+  for (int i = t; i < sort::kLowBins; i += kChunk) hh[(size_t)i * m.nchunks + chunk] = s_hist[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLAN 1/3, fast variant (geometry.cuh: FastRay): same outputs as ls_plan_runs_kernel for pixel chunks
+// whose camera / pixels qualify; chunk_done[frame_chunk] tells the general kernel to skip them.
+// ~half the instructions per point and few enough registers for every CTA of a batch to be resident
+// at once (one wave).  grid (nchunks, B), 128 threads.
+// ---------------------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void __launch_bounds__(kChunk, 9)
+ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *__restrict__ v_tab,
+                         const float *__restrict__ z_tab, const float *__restrict__ ida_inv,
+                         const float *__restrict__ mv, const float *__restrict__ me,
+                         const float *__restrict__ bda, const float *__restrict__ ref_h, geom::Grid grid,
+                         int *__restrict__ run_cnt, int *__restrict__ run_vox, int *__restrict__ run_d,
+                         int *__restrict__ hist1, int *__restrict__ chunk_done) {
+  __shared__ geom::Camera cam;
+  __shared__ int s_hist[sort::kLowBins];
+  __shared__ int s_fast;
+  extern __shared__ float z_s[];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int bn = b * m.Nc + n;
+  const int t = threadIdx.x;
+  const int frame_chunk = b * m.nchunks + chunk;
+  geom::load_camera(&cam, ida_inv, mv, me, bda, ref_h, bn, b);
+  bool z_ok = true;
+  for (int d = t; d < m.D; d += kChunk) {
+    const float z = z_tab[d];
+    z_s[d] = z;
+    z_ok = z_ok && (fabsf(z) < INFINITY);
+  }
+  for (int i = t; i < sort::kLowBins; i += kChunk) s_hist[i] = 0;
+  if (!__syncthreads_and(z_ok)) {  // (also publishes cam / z_s / s_hist)
+    if (t == 0) chunk_done[frame_chunk] = 0;
+    return;
+  }
+  if (t == 0) s_fast = geom::camera_is_fast(cam) ? 1 : 0;
+  __syncthreads();
+  if (!s_fast) {
+    if (t == 0) chunk_done[frame_chunk] = 0;
+    return;
+  }
+  const int p = ci * kChunk + t;
+  int r = 0;
+  bool bad = false;
+  if (p < m.P) {
+    const int h = p / m.fW, w = p - h * m.fW;
+    geom::FastRay<ARITH> ray;
+    bad = !ray.init(cam, u_tab[w], v_tab[h], z_s[0]);
+    float a2[4], mer[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a2[i] = cam.A[8 + i];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) mer[i] = cam.Me[i];
+    const float rh = cam.ref_h;
+    const bool check_finite = cam.has_bda != 0;
+    int cur = -1, d0 = 0;
+    auto step = [&](int d, int vox) {
+      if (vox != cur) {
+        if (cur >= 0) {
+          const size_t s = ell_slot(frame_chunk, m.D, r, t);
+          run_vox[s] = cur;
+          run_d[s] = d0 | (d << 16);
+          atomicAdd(&s_hist[cur & (sort::kLowBins - 1)], 1);
+          ++r;
+        }
+        cur = vox;
+        d0 = d;
+      }
+    };
+    int d = 0;
+    for (; d + 2 <= m.D; d += 2) {
+      const int v0 = ray.voxel(a2, mer, rh, check_finite, grid, z_s[d], bad);
+      const int v1 = ray.voxel(a2, mer, rh, check_finite, grid, z_s[d + 1], bad);
+      step(d, v0);
+      step(d + 1, v1);
+    }
+    if (d < m.D) {
+      step(d, ray.voxel(a2, mer, rh, check_finite, grid, z_s[d], bad));
+      ++d;
+    }
+    step(m.D, -2);  // sentinel closes the last run
+  }
+  run_cnt[(size_t)frame_chunk * kChunk + t] = r;
+  const int any_bad = __syncthreads_or(bad);
+  if (t == 0) chunk_done[frame_chunk] = any_bad ? 0 : 1;
   int *hh = hist1 + (size_t)b * sort::kLowBins * m.nchunks;
   for (int i = t; i < sort::kLowBins; i += kChunk) hh[(size_t)i * m.nchunks + chunk] = s_hist[i];
 }
@@ -536,11 +627,14 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   const int tile_lo = s_rp[0], tile_hi = s_rp[kTileV];
   float *out = bev + (size_t)b * m.C * m.V + v0;
 
+  // thread <-> (channel row c0 + 16*i, 16-byte chunk q) of the tile for the copy-out loops
+  const int q = tid & 15, c0 = tid >> 4;
   if (tile_hi == tile_lo) {  // no point falls into this tile: zero fill
     if (vec_out) {
-      for (int i = tid; i < m.C * (kTileV / 4); i += kRedWarps * 32) {
-        const int c = i >> 4, q = i & 15;
-        if (4 * q < nv) stg_stream_f4(reinterpret_cast<float4 *>(out + (size_t)c * m.V) + q, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (4 * q < nv) {
+        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)c0 * m.V) + q;
+        const size_t step = (size_t)4 * m.V;  // 16 channel rows, in float4 units
+        for (int c = c0; c < m.C; c += 16, o4 += step) stg_stream_f4(o4, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     } else {
       for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
@@ -586,21 +680,22 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
     run_stream<CT, G, NV, false>(lane_rows, ent, jb[0], jb[1], tile_lane, l & 7, kBoxBytes);
   __syncthreads();
 
-  // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line
+  // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line.
+  // Rows advance by 16 per step, so (row & 7) and with it the swizzled chunk position never change.
   if (vec_out) {
-    for (int i = tid; i < m.C * (kTileV / 4); i += kRedWarps * 32) {
-      const int c = i >> 4, q = i & 15;
-      if (4 * q < nv) {
-        const float4 t = *reinterpret_cast<const float4 *>(tile + (q >> 3) * kBoxBytes + tile_chunk(c, q & 7));
-        stg_stream_f4(reinterpret_cast<float4 *>(out + (size_t)c * m.V) + q, t);
-      }
+    if (4 * q < nv) {
+      const unsigned char *t4 = tile + (q >> 3) * kBoxBytes + tile_chunk(c0, q & 7);
+      float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)c0 * m.V) + q;
+      const size_t step = (size_t)4 * m.V;
+      for (int c = c0; c < m.C; c += 16, o4 += step, t4 += 16 * 128)
+        stg_stream_f4(o4, *reinterpret_cast<const float4 *>(t4));
     }
   } else {
     for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
-      const int c = i >> 6, j = i & 63, q = j >> 2;
+      const int c = i >> 6, j = i & 63, qq = j >> 2;
       if (j < nv)
         stg_stream_f1(out + (size_t)c * m.V + j,
-                      *reinterpret_cast<const float *>(tile + (q >> 3) * kBoxBytes + tile_chunk(c, q & 7) + 4 * (j & 3)));
+                      *reinterpret_cast<const float *>(tile + (qq >> 3) * kBoxBytes + tile_chunk(c, qq & 7) + 4 * (j & 3)));
     }
   }
 }
@@ -899,18 +994,20 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
 
   dim3 gc(m.nchunks, m.B);
   const size_t zsm = sizeof(float) * m.D;
-  if (desc->arith == SGV3D_ARITH_PAIR)
-    ls_plan_runs_kernel<SGV3D_ARITH_PAIR><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
-                                                                m_ego, bda, ref_heights, grid, w.run_cnt,
-                                                                w.run_vox, w.run_d, w.hist1);
-  else if (desc->arith == SGV3D_ARITH_FMA)
-    ls_plan_runs_kernel<SGV3D_ARITH_FMA><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
-                                                               m_ego, bda, ref_heights, grid, w.run_cnt,
-                                                               w.run_vox, w.run_d, w.hist1);
-  else
-    ls_plan_runs_kernel<SGV3D_ARITH_SEQ><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual,
-                                                               m_ego, bda, ref_heights, grid, w.run_cnt,
-                                                               w.run_vox, w.run_d, w.hist1);
+#define SGV3D_PLAN_RUNS(A)                                                                                  \
+  do {                                                                                                      \
+    ls_plan_runs_fast_kernel<A><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego,   \
+                                                        bda, ref_heights, grid, w.run_cnt, w.run_vox,       \
+                                                        w.run_d, w.hist1, w.chunk_done);                    \
+    SGV3D_CHECK_LAUNCH("ls_plan_runs_fast_kernel");                                                         \
+    ls_plan_runs_kernel<A><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda,   \
+                                                   ref_heights, grid, w.run_cnt, w.run_vox, w.run_d,        \
+                                                   w.hist1, w.chunk_done);                                  \
+  } while (0)
+  if (desc->arith == SGV3D_ARITH_PAIR) SGV3D_PLAN_RUNS(SGV3D_ARITH_PAIR);
+  else if (desc->arith == SGV3D_ARITH_FMA) SGV3D_PLAN_RUNS(SGV3D_ARITH_FMA);
+  else SGV3D_PLAN_RUNS(SGV3D_ARITH_SEQ);
+#undef SGV3D_PLAN_RUNS
   SGV3D_CHECK_LAUNCH("ls_plan_runs_kernel");
   sort::scan_hist_kernel<<<m.B, sort::kScanThreads, 0, s>>>(w.hist1, sort::kLowBins, m.nchunks, nullptr, 0,
                                                             w.count);
