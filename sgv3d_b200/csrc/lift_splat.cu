@@ -8,10 +8,15 @@
 // nnz = #runs (3-7x fewer than points; SURVEY.md §7 hard part 3).
 //
 //   PLAN   (index; depends on calibration + grid only)
-//     ls_plan_runs_kernel     thread/pixel walks D: bit-exact geometry -> voxel id -> run-length
-//                             encoding, emitted pixel-major in an ELL layout; digit histogram
-//     scan / scatter / hist / scan / scatter   stable 2-pass radix sort of the runs by voxel
-//     row_ptr_kernel          CSR offsets per voxel + inverse permutation (run -> sorted slot)
+//     ls_plan_runs_*_kernel   thread/pixel walks D: bit-exact geometry -> voxel id -> run-length
+//                             encoding, emitted pixel-major in an ELL layout; per-chunk histogram of the
+//                             runs over 64-voxel tiles
+//     ls_scan_tiles_kernel    per frame: exclusive scan of the histograms (over chunks, then over tiles)
+//     ls_scatter_tiles_kernel stable scatter of the runs into per-tile buckets (MSD pass: one digit = the tile)
+//     ls_finish_tiles_kernel  per tile: stable counting sort of its bucket by voxel-in-tile, CSR offsets per
+//                             voxel, inverse permutation (run -> sorted slot)
+//     Ties keep the canonical (chunk, warp, run index, lane) order => the per-voxel summation order is a
+//     pure function of the calibration: deterministic, no floating-point atomics.
 //   FORWARD (values)
 //     transpose_pad_kernel    context NCHW -> one 16B-aligned row per pixel
 //     ls_weights_kernel       [softmax over D fused] w[run] = sum_{d in run} p[d,pixel]; the height
@@ -56,14 +61,21 @@ struct Dims {
   int G, NV;    // row layout: G lanes per row, NV 4-element vectors per lane (transpose.cuh)
   int esize;    // bytes per context element (4 fp32, 2 bf16)
   int cap;      // max runs per frame (= ELL slots per frame)
-  int bins2, nblk2;
+  int ntiles;   // ceil(V / 64) reduce tiles per frame
   int logits;             // height tensor holds raw logits (softmax over D fused)
   long long hs, cs;       // element strides between consecutive cameras of height / context
   long long ghs, gcs;     // same for grad_height / grad_context
 };
 
+// Run in its tile bucket (after the MSD pass, before the per-tile finish).
+struct __align__(8) BucketEnt {
+  unsigned key;  // frame-local pixel row (n*P + p) << 6 | voxel index inside the tile
+  int slot;      // frame-local ELL slot of the run
+};
+
 struct Workspace {
-  int *count, *run_cnt, *run_vox, *run_d, *run_dst, *hist1, *keys1, *pay1, *hist2, *keys2, *row_ptr, *chunk_done;
+  int *run_cnt, *run_vox, *run_d, *run_dst, *hist, *tile_ptr, *row_ptr, *chunk_done;
+  BucketEnt *bucket;
   Entry *vm_ent;  // sorted (row offset, weight) pairs
   float *w_pm, *gw_pm, *gT, *gctxT;
   void *ctxT;
@@ -89,8 +101,7 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   m.Cpad = 4 * m.G * m.NV;
   m.esize = d->ctx_dtype == SGV3D_DTYPE_BF16 ? 2 : 4;
   m.cap = m.nchunks * kChunk * m.D;
-  m.bins2 = (m.V >> sort::kLowBits) + 1;
-  m.nblk2 = ceil_div(m.cap, sort::kItemsPerBlock);
+  m.ntiles = ceil_div(m.V, 64);
   m.logits = d->height_is_logits;
   m.hs = d->height_batch_stride ? d->height_batch_stride : (long long)m.D * m.P;
   m.cs = d->ctx_batch_stride ? d->ctx_batch_stride : (long long)m.C * m.P;
@@ -105,17 +116,14 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   Workspace w;
   Carver c(ws);
   const size_t B = m.B, slots = (size_t)m.B * m.cap;
-  w.count = c.take<int>(B);
   w.chunk_done = c.take<int>(B * m.nchunks);
   w.run_cnt = c.take<int>(B * m.nchunks * kChunk);
   w.run_vox = c.take<int>(slots);
   w.run_d = c.take<int>(slots);
   w.run_dst = c.take<int>(slots);
-  w.hist1 = c.take<int>(B * sort::kLowBins * m.nchunks);
-  w.keys1 = c.take<int>(slots);
-  w.pay1 = c.take<int>(slots);
-  w.hist2 = c.take<int>(B * m.bins2 * m.nblk2);
-  w.keys2 = c.take<int>(slots);
+  w.hist = c.take<int>(B * m.nchunks * m.ntiles);
+  w.tile_ptr = c.take<int>(B * (m.ntiles + 1));
+  w.bucket = reinterpret_cast<BucketEnt *>(c.take<int2>(slots));
   w.vm_ent = reinterpret_cast<Entry *>(c.take<int2>(slots));
   w.row_ptr = c.take<int>(B * (m.V + 1));
   w.w_pm = c.take<float>(slots);
@@ -135,7 +143,7 @@ __device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t)
 }
 
 // ---------------------------------------------------------------------------------------------
-// PLAN 1/3: geometry -> voxel id per height bin -> runs.  grid (nchunks, B), 128 threads.
+// PLAN 1/4: geometry -> voxel id per height bin -> runs.  grid (nchunks, B), 128 threads.
 // Pure ALU work (no global reads besides three tiny tables); two bins per iteration for ILP.
 // ---------------------------------------------------------------------------------------------
 template <int ARITH>
@@ -145,10 +153,10 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
                     const float *__restrict__ mv, const float *__restrict__ me,
                     const float *__restrict__ bda, const float *__restrict__ ref_h, geom::Grid grid,
                     int *__restrict__ run_cnt, int *__restrict__ run_vox, int *__restrict__ run_d,
-                    int *__restrict__ hist1, const int *__restrict__ chunk_done) {
+                    int *__restrict__ hist, const int *__restrict__ chunk_done) {
   __shared__ geom::Camera cam;
-  __shared__ int s_hist[sort::kLowBins];
-  extern __shared__ float z_s[];
+  extern __shared__ float z_s[];                           // [D] height-bin values, then
+  int *s_hist = reinterpret_cast<int *>(z_s + m.D);        // [ntiles] runs per reduce tile
   const int b = blockIdx.y, chunk = blockIdx.x;
   if (chunk_done[b * m.nchunks + chunk]) return;  // the fast kernel already produced this chunk
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
@@ -156,7 +164,7 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
   const int t = threadIdx.x;
   geom::load_camera(&cam, ida_inv, mv, me, bda, ref_h, bn, b);
   for (int d = t; d < m.D; d += kChunk) z_s[d] = z_tab[d];
-  for (int i = t; i < sort::kLowBins; i += kChunk) s_hist[i] = 0;
+  for (int i = t; i < m.ntiles; i += kChunk) s_hist[i] = 0;
   __syncthreads();
   const int frame_chunk = b * m.nchunks + chunk;
   const int p = ci * kChunk + t;
@@ -172,7 +180,7 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
           const size_t s = ell_slot(frame_chunk, m.D, r, t);
           run_vox[s] = cur;
           run_d[s] = d0 | (d << 16);
-          atomicAdd(&s_hist[cur & (sort::kLowBins - 1)], 1);
+          atomicAdd(&s_hist[cur >> 6], 1);
           ++r;
         }
         cur = vox;
@@ -194,12 +202,12 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
   }
   run_cnt[(size_t)frame_chunk * kChunk + t] = r;
   __syncthreads();
-  int *hh = hist1 + (size_t)b * sort::kLowBins * m.nchunks;
-  for (int i = t; i < sort::kLowBins; i += kChunk) hh[(size_t)i * m.nchunks + chunk] = s_hist[i];
+  int *hh = hist + (size_t)frame_chunk * m.ntiles;
+  for (int i = t; i < m.ntiles; i += kChunk) hh[i] = s_hist[i];
 }
 
 // ---------------------------------------------------------------------------------------------
-// PLAN 1/3, fast variant (geometry.cuh: FastRay): same outputs as ls_plan_runs_kernel for pixel chunks
+// PLAN 1/4, fast variant (geometry.cuh: FastRay): same outputs as ls_plan_runs_kernel for pixel chunks
 // whose camera / pixels qualify; chunk_done[frame_chunk] tells the general kernel to skip them.
 // ~half the instructions per point and few enough registers for every CTA of a batch to be resident
 // at once (one wave).  grid (nchunks, B), 128 threads.
@@ -211,11 +219,11 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
                          const float *__restrict__ mv, const float *__restrict__ me,
                          const float *__restrict__ bda, const float *__restrict__ ref_h, geom::Grid grid,
                          int *__restrict__ run_cnt, int *__restrict__ run_vox, int *__restrict__ run_d,
-                         int *__restrict__ hist1, int *__restrict__ chunk_done) {
+                         int *__restrict__ hist, int *__restrict__ chunk_done) {
   __shared__ geom::Camera cam;
-  __shared__ int s_hist[sort::kLowBins];
   __shared__ int s_fast;
   extern __shared__ float z_s[];
+  int *s_hist = reinterpret_cast<int *>(z_s + m.D);
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int bn = b * m.Nc + n;
@@ -228,7 +236,7 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
     z_s[d] = z;
     z_ok = z_ok && (fabsf(z) < INFINITY);
   }
-  for (int i = t; i < sort::kLowBins; i += kChunk) s_hist[i] = 0;
+  for (int i = t; i < m.ntiles; i += kChunk) s_hist[i] = 0;
   if (!__syncthreads_and(z_ok)) {  // (also publishes cam / z_s / s_hist)
     if (t == 0) chunk_done[frame_chunk] = 0;
     return;
@@ -260,7 +268,7 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
           const size_t s = ell_slot(frame_chunk, m.D, r, t);
           run_vox[s] = cur;
           run_d[s] = d0 | (d << 16);
-          atomicAdd(&s_hist[cur & (sort::kLowBins - 1)], 1);
+          atomicAdd(&s_hist[cur >> 6], 1);
           ++r;
         }
         cur = vox;
@@ -283,13 +291,86 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
   run_cnt[(size_t)frame_chunk * kChunk + t] = r;
   const int any_bad = __syncthreads_or(bad);
   if (t == 0) chunk_done[frame_chunk] = any_bad ? 0 : 1;
-  int *hh = hist1 + (size_t)b * sort::kLowBins * m.nchunks;
-  for (int i = t; i < sort::kLowBins; i += kChunk) hh[(size_t)i * m.nchunks + chunk] = s_hist[i];
+  int *hh = hist + (size_t)frame_chunk * m.ntiles;
+  for (int i = t; i < m.ntiles; i += kChunk) hh[i] = s_hist[i];
 }
 
 // ---------------------------------------------------------------------------------------------
-// PLAN 2/3: first radix pass straight out of the ELL layout.  Block = chunk, warp w owns the
-// pixels t = 32w + lane, iteration = run index r.  Payload = frame-local ELL slot.
+// PLAN 2/4: per frame, turn the per-chunk tile histograms hist[chunk][tile] into scatter bases:
+//   hist[chunk][tile] <- number of runs of this tile in chunks < chunk   (exclusive, in place)
+//   tile_ptr[tile]    <- number of runs in tiles < tile;  tile_ptr[ntiles] = runs of the frame
+// grid (B), 1024 threads.  Thread = tile for the chunk walk (coalesced rows, 8 loads in flight).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxTiles = 4096;  // V <= 262144 voxels per frame (512 x 512)
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads)
+ls_scan_tiles_kernel(Dims m, int *__restrict__ hist, int *__restrict__ tile_ptr) {
+  __shared__ int s_tot[kMaxTiles];
+  __shared__ int s_warp[kScanThreads / 32];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  int *h = hist + (size_t)b * m.nchunks * m.ntiles;
+  for (int bin = t; bin < kMaxTiles; bin += kScanThreads) {
+    int run = 0;
+    if (bin < m.ntiles) {
+      int c = 0;
+      for (; c + 8 <= m.nchunks; c += 8) {
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = h[(size_t)(c + u) * m.ntiles + bin];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          h[(size_t)(c + u) * m.ntiles + bin] = run;
+          run += v[u];
+        }
+      }
+      for (; c < m.nchunks; ++c) {
+        const int v = h[(size_t)c * m.ntiles + bin];
+        h[(size_t)c * m.ntiles + bin] = run;
+        run += v;
+      }
+    }
+    s_tot[bin] = run;
+  }
+  __syncthreads();
+  // exclusive scan over the tiles: thread t owns tiles [4t, 4t + 4)
+  int v[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = s_tot[4 * t + k];
+    sum += v[k];
+  }
+  int x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    const int w = s_warp[lane];
+    int xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    s_warp[lane] = xs - w;
+  }
+  __syncthreads();
+  int excl = s_warp[wid] + x - sum;
+  int *tp = tile_ptr + (size_t)b * (m.ntiles + 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (4 * t + k <= m.ntiles) tp[4 * t + k] = excl;  // tiles >= ntiles hold 0 runs: entry ntiles = total
+    excl += v[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLAN 3/4: stable scatter of the runs into per-tile buckets, straight out of the ELL layout.
+// Block = chunk, warp w owns the pixels t = 32w + lane, iteration = run index r.
 // ---------------------------------------------------------------------------------------------
 struct EllInput {
   const int *run_vox;
@@ -306,11 +387,32 @@ struct EllInput {
   }
 };
 
+struct TileOf {
+  __device__ __forceinline__ int operator()(int vox) const { return vox >> 6; }
+};
+struct TileBase {
+  const int *tile_ptr, *hist_chunk;
+  __device__ __forceinline__ int operator()(int tile) const { return tile_ptr[tile] + hist_chunk[tile]; }
+};
+struct PlaceBucket {
+  BucketEnt *bucket;
+  int D, cpc, P;
+  __device__ __forceinline__ void operator()(int pos, int vox, int slot) const {
+    const int t = slot & (kChunk - 1);
+    const int chunk = (slot / kChunk) / D;
+    const int n = chunk / cpc, ci = chunk - n * cpc;
+    BucketEnt e;
+    e.key = ((unsigned)(n * P + ci * kChunk + t) << 6) | (unsigned)(vox & 63);
+    e.slot = slot;
+    bucket[pos] = e;
+  }
+};
+
 __global__ void __launch_bounds__(kChunk)
-ls_scatter_ell_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_vox,
-                      const int *__restrict__ gbase1, int *__restrict__ keys1,
-                      int *__restrict__ pay1) {
-  __shared__ int s_cnt[(kChunk / 32) * sort::kLowBins];
+ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_vox,
+                        const int *__restrict__ hist, const int *__restrict__ tile_ptr,
+                        BucketEnt *__restrict__ bucket) {
+  extern __shared__ int s_cnt[];  // [kChunk / 32][ntiles]
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int frame_chunk = b * m.nchunks + chunk;
   EllInput in;
@@ -320,39 +422,105 @@ ls_scatter_ell_kernel(Dims m, const int *__restrict__ run_cnt, const int *__rest
   in.D = m.D;
   in.cnt = run_cnt[(size_t)frame_chunk * kChunk + threadIdx.x];
   in.warp_max = __reduce_max_sync(0xffffffffu, in.cnt);
-  sort::stable_scatter_block<kChunk / 32>(in, sort::DigitOf<0, sort::kLowBins - 1>(), sort::kLowBins,
-                                          gbase1 + (size_t)b * sort::kLowBins * m.nchunks, m.nchunks,
-                                          chunk, s_cnt,
-                                          sort::PlaceKeyPayload{keys1 + (size_t)b * m.cap, pay1 + (size_t)b * m.cap});
+  sort::stable_scatter_block<kChunk / 32>(
+      in, TileOf(), m.ntiles,
+      TileBase{tile_ptr + (size_t)b * (m.ntiles + 1), hist + (size_t)frame_chunk * m.ntiles}, s_cnt,
+      PlaceBucket{bucket + (size_t)b * m.cap, m.D, m.cpc, m.P});
 }
 
-// PLAN 3/3: placement functor of the second radix pass.  Besides the sorted key it records, per
-// sorted position, the context-row offset of the run's pixel, and the inverse permutation
-// (ELL slot -> sorted position) that the forward weights pass scatters through.
-struct PlanPlace {
-  int *keys2;
-  Entry *vm_ent;
-  int *run_dst;
-  int D, cpc, P, row_bytes;
-  __device__ __forceinline__ void operator()(int pos, int key, int slot) const {
-    keys2[pos] = key;
-    run_dst[slot] = pos;
-    const int t = slot & (kChunk - 1);
-    const int chunk = (slot / kChunk) / D;
-    const int n = chunk / cpc, ci = chunk - n * cpc;
-    vm_ent[pos].off = (unsigned)(n * P + ci * kChunk + t) * (unsigned)row_bytes | (unsigned)(key & 63);
+// ---------------------------------------------------------------------------------------------
+// PLAN 4/4: per tile, stable counting sort of the bucket by voxel-in-tile (6 bits).  Emits, per
+// sorted position, the context-row offset of the run's pixel OR-ed with the voxel-in-tile index, the
+// inverse permutation (ELL slot -> sorted position) that the forward weights pass scatters through,
+// and the CSR offsets of the tile's 64 voxels.  grid (ntiles, B), 128 threads; warp w owns the w-th
+// quarter of the bucket (contiguous => the canonical order is kept).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFinWarps = 4;
+
+__global__ void __launch_bounds__(kFinWarps * 32)
+ls_finish_tiles_kernel(Dims m, unsigned row_bytes, const int *__restrict__ tile_ptr,
+                       const BucketEnt *__restrict__ bucket, Entry *__restrict__ vm_ent,
+                       int *__restrict__ run_dst, int *__restrict__ row_ptr) {
+  __shared__ int s_cnt[kFinWarps][64];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1);
+  const int lo = tp[tile], hi = tp[tile + 1];
+  int *rp = row_ptr + (size_t)b * (m.V + 1);
+  const int v0 = tile * 64;
+  if (hi == lo) {
+    if (t < 64 && v0 + t < m.V) rp[v0 + t] = lo;
+    if (t == 64 && tile == m.ntiles - 1) rp[m.V] = hi;
+    return;
   }
-};
-struct PlanPlaceFactory {
-  int *keys2;
-  Entry *vm_ent;
-  int *run_dst;
-  int D, cpc, P, row_bytes, cap;
-  __device__ __forceinline__ PlanPlace operator()(int frame) const {
-    const size_t o = (size_t)frame * cap;
-    return PlanPlace{keys2 + o, vm_ent + o, run_dst + o, D, cpc, P, row_bytes};
+  for (int i = t; i < kFinWarps * 64; i += kFinWarps * 32) (&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int n = hi - lo;
+  const int per = (n + kFinWarps - 1) / kFinWarps;
+  const int wb = lo + min(wid * per, n), we = lo + min((wid + 1) * per, n);
+  const BucketEnt *bk = bucket + (size_t)b * m.cap;
+  int *my = s_cnt[wid];
+  for (int i = wb + lane; i < we; i += 32) atomicAdd(&my[bk[i].key & 63u], 1);
+  __syncthreads();
+  if (wid == 0) {  // 64 voxels, two per lane: totals -> exclusive scan -> per-warp bases
+    int c[2][kFinWarps], tot[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      tot[k] = 0;
+#pragma unroll
+      for (int w = 0; w < kFinWarps; ++w) {
+        c[k][w] = s_cnt[w][2 * lane + k];
+        tot[k] += c[k][w];
+      }
+    }
+    const int sum = tot[0] + tot[1];
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    int base = lo + x - sum;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (v0 + 2 * lane + k < m.V) rp[v0 + 2 * lane + k] = base;
+#pragma unroll
+      for (int w = 0; w < kFinWarps; ++w) {
+        s_cnt[w][2 * lane + k] = base;
+        base += c[k][w];
+      }
+    }
+    if (lane == 31 && tile == m.ntiles - 1) rp[m.V] = hi;
   }
-};
+  __syncthreads();
+  const unsigned lt = lanemask_lt();
+  Entry *ve = vm_ent + (size_t)b * m.cap;
+  int *rd = run_dst + (size_t)b * m.cap;
+  for (int i0 = wb; i0 < we; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < we;
+    BucketEnt e;
+    e.key = 0; e.slot = 0;
+    if (valid) e = bk[i];
+    // invalid lanes get a private pseudo-digit so that they never match a real one
+    const int dig = valid ? (int)(e.key & 63u) : 64 + lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, dig);
+    const int leader = __ffs(peers) - 1;
+    const int rank = __popc(peers & lt);
+    int base = 0;
+    if (valid && lane == leader) {
+      base = my[dig];
+      my[dig] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) {
+      const int pos = base + rank;
+      ve[pos].off = (e.key >> 6) * row_bytes | (e.key & 63u);
+      rd[e.slot] = pos;
+    }
+    __syncwarp();
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Column staging: the D x 128 block of height values (or logits) of one pixel chunk goes to shared
@@ -859,8 +1027,8 @@ int validate(const sgv3d_lift_splat_desc *d, const char *who) {
   SGV3D_REQUIRE(d->B <= 65535, "%s: B > 65535", who);
   SGV3D_REQUIRE(d->D <= 400, "%s: D=%d > 400 unsupported (height columns are staged in shared memory)", who, d->D);
   SGV3D_REQUIRE(d->C <= 256, "%s: C=%d > 256 unsupported by the fused path", who, d->C);
-  SGV3D_REQUIRE((long long)d->X * d->Y < (long long)sort::kMaxHighBins << sort::kLowBits,
-                "%s: X*Y exceeds %d voxels per frame", who, sort::kMaxHighBins << sort::kLowBits);
+  SGV3D_REQUIRE((long long)d->X * d->Y <= (long long)kMaxTiles * 64,
+                "%s: X*Y exceeds %d voxels per frame", who, kMaxTiles * 64);
   SGV3D_REQUIRE(d->arith >= SGV3D_ARITH_SEQ && d->arith <= SGV3D_ARITH_PAIR, "%s: bad arith", who);
   SGV3D_REQUIRE(d->ctx_dtype == SGV3D_DTYPE_F32 || d->ctx_dtype == SGV3D_DTYPE_BF16, "%s: bad ctx_dtype", who);
   SGV3D_REQUIRE(d->height_is_logits == 0 || d->height_is_logits == 1, "%s: bad height_is_logits", who);
@@ -868,6 +1036,10 @@ int validate(const sgv3d_lift_splat_desc *d, const char *who) {
                     d->grad_ctx_batch_stride >= 0, "%s: negative batch stride", who);
   const long long slots = (long long)d->Nc * ceil_div(d->fH * d->fW, kChunk) * kChunk * d->D;
   SGV3D_REQUIRE(slots < (1ll << 31), "%s: more than 2^31 height-bin slots per frame", who);
+  // a frame's channels-last context rows are addressed by 32-bit byte offsets, pixel rows by 26 bits
+  SGV3D_REQUIRE((long long)d->Nc * d->fH * d->fW < (1ll << 26) &&
+                    (long long)d->Nc * d->fH * d->fW * 4 * 256 < (1ll << 32),
+                "%s: more than 2^22 pixels per frame", who);
   return SGV3D_OK;
 }
 
@@ -993,44 +1165,31 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   grid.rcp_size[1] = 1.0f / grid.size[1];
 
   dim3 gc(m.nchunks, m.B);
-  const size_t zsm = sizeof(float) * m.D;
+  const size_t zsm = sizeof(float) * m.D + sizeof(int) * m.ntiles;
 #define SGV3D_PLAN_RUNS(A)                                                                                  \
   do {                                                                                                      \
     ls_plan_runs_fast_kernel<A><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego,   \
                                                         bda, ref_heights, grid, w.run_cnt, w.run_vox,       \
-                                                        w.run_d, w.hist1, w.chunk_done);                    \
+                                                        w.run_d, w.hist, w.chunk_done);                     \
     SGV3D_CHECK_LAUNCH("ls_plan_runs_fast_kernel");                                                         \
     ls_plan_runs_kernel<A><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda,   \
                                                    ref_heights, grid, w.run_cnt, w.run_vox, w.run_d,        \
-                                                   w.hist1, w.chunk_done);                                  \
+                                                   w.hist, w.chunk_done);                                   \
   } while (0)
   if (desc->arith == SGV3D_ARITH_PAIR) SGV3D_PLAN_RUNS(SGV3D_ARITH_PAIR);
   else if (desc->arith == SGV3D_ARITH_FMA) SGV3D_PLAN_RUNS(SGV3D_ARITH_FMA);
   else SGV3D_PLAN_RUNS(SGV3D_ARITH_SEQ);
 #undef SGV3D_PLAN_RUNS
   SGV3D_CHECK_LAUNCH("ls_plan_runs_kernel");
-  sort::scan_hist_kernel<<<m.B, sort::kScanThreads, 0, s>>>(w.hist1, sort::kLowBins, m.nchunks, nullptr, 0,
-                                                            w.count);
-  SGV3D_CHECK_LAUNCH("scan_hist_kernel(1)");
-  ls_scatter_ell_kernel<<<gc, kChunk, 0, s>>>(m, w.run_cnt, w.run_vox, w.hist1, w.keys1, w.pay1);
-  SGV3D_CHECK_LAUNCH("ls_scatter_ell_kernel");
-  // the number of runs per frame lives on the device: size the second pass by a grid-stride loop
-  const int gx2 = m.nblk2 < 96 ? m.nblk2 : 96;
-  dim3 g2(gx2, m.B);
-  sort::hist_contiguous_kernel<sort::kLowBits><<<g2, sort::kThreads, sizeof(int) * m.bins2, s>>>(
-      w.keys1, (size_t)m.cap, w.count, 0, m.bins2, m.nblk2, w.hist2);
-  SGV3D_CHECK_LAUNCH("hist_contiguous_kernel");
-  sort::scan_hist_kernel<<<m.B, sort::kScanThreads, 0, s>>>(w.hist2, m.bins2, m.nblk2, w.count,
-                                                            sort::kItemsPerBlock, nullptr);
-  SGV3D_CHECK_LAUNCH("scan_hist_kernel(2)");
-  sort::scatter_contiguous_kernel<sort::kLowBits, 0xFFFFFF, PlanPlaceFactory>
-      <<<g2, sort::kThreads, sizeof(int) * sort::kWarps * m.bins2, s>>>(
-          w.keys1, w.pay1, (size_t)m.cap, w.count, 0, m.bins2, w.hist2, m.nblk2,
-          PlanPlaceFactory{w.keys2, w.vm_ent, w.run_dst, m.D, m.cpc, m.P, m.Cpad * m.esize, m.cap});
-  SGV3D_CHECK_LAUNCH("scatter_contiguous_kernel(2)");
-  const int gxr = ceil_div(m.cap, 256) < 128 ? ceil_div(m.cap, 256) : 128;
-  sort::row_ptr_kernel<<<dim3(gxr, m.B), 256, 0, s>>>(w.keys2, (size_t)m.cap, w.count, 0, m.V, w.row_ptr);
-  SGV3D_CHECK_LAUNCH("row_ptr_kernel");
+  ls_scan_tiles_kernel<<<m.B, kScanThreads, 0, s>>>(m, w.hist, w.tile_ptr);
+  SGV3D_CHECK_LAUNCH("ls_scan_tiles_kernel");
+  const size_t csm = sizeof(int) * (kChunk / 32) * m.ntiles;
+  if (int rc = set_smem(ls_scatter_tiles_kernel, csm)) return rc;
+  ls_scatter_tiles_kernel<<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
+  SGV3D_CHECK_LAUNCH("ls_scatter_tiles_kernel");
+  ls_finish_tiles_kernel<<<dim3(m.ntiles, m.B), kFinWarps * 32, 0, s>>>(
+      m, (unsigned)(m.Cpad * m.esize), w.tile_ptr, w.bucket, w.vm_ent, w.run_dst, w.row_ptr);
+  SGV3D_CHECK_LAUNCH("ls_finish_tiles_kernel");
   return SGV3D_OK;
 }
 

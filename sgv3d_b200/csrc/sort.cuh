@@ -134,10 +134,17 @@ struct PlaceKeyPayload {
   }
 };
 
-template <int NWARPS, typename In, typename DigitFn, typename Place>
+// base_of(d) = global position of the block's first item with digit d (exclusive scan of the
+// per-block digit histograms).  BinMajorBase reads it from a scan_hist_kernel table.
+struct BinMajorBase {
+  const int *gbase_frame;
+  int nblk_max, blk;
+  __device__ __forceinline__ int operator()(int d) const { return gbase_frame[(size_t)d * nblk_max + blk]; }
+};
+
+template <int NWARPS, typename In, typename DigitFn, typename BaseOf, typename Place>
 __device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit_of, int bins,
-                                                     const int *__restrict__ gbase_frame,
-                                                     int nblk_max, int blk, int *s_cnt /*[NWARPS][bins]*/,
+                                                     const BaseOf &base_of, int *s_cnt /*[NWARPS][bins]*/,
                                                      const Place &place) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   for (int i = t; i < NWARPS * bins; i += NWARPS * kWarp) s_cnt[i] = 0;
@@ -155,7 +162,7 @@ __device__ __forceinline__ void stable_scatter_block(const In &in, DigitFn digit
   }
   __syncthreads();
   for (int d = t; d < bins; d += NWARPS * kWarp) {
-    int base = gbase_frame[(size_t)d * nblk_max + blk];
+    int base = base_of(d);
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
       const int c = s_cnt[w * bins + d];
@@ -231,7 +238,7 @@ scatter_contiguous_kernel(const int *__restrict__ keys_in, const int *__restrict
                        payload_in ? payload_in + (size_t)frame * frame_stride_in : nullptr,
                        blk * kItemsPerBlock, n};
     stable_scatter_block<kWarps>(in, DigitOf<SHIFT, MASK>(), bins,
-                                 gbase + (size_t)frame * bins * nblk_max, nblk_max, blk, s_cnt, place);
+                                 BinMajorBase{gbase + (size_t)frame * bins * nblk_max, nblk_max, blk}, s_cnt, place);
     __syncthreads();
   }
 }
