@@ -16,7 +16,7 @@ library, or with CPU tensors, raises.
 """
 from .shapes import SHAPES, LiftSplatShape, get_shape  # noqa: F401
 from .ops.voxel_pooling import VoxelPooling, voxel_pooling  # noqa: F401
-from .view_transform import (LiftSplat, LiftSplatPlan, build_frustum, camera_matrices,  # noqa: F401
-                             geometry_indices, lift_splat)
+from .view_transform import (LiftSplat, LiftSplatGraph, LiftSplatPlan, build_frustum,  # noqa: F401
+                             camera_matrices, geometry_indices, lift_splat)
 
 __version__ = "0.1.0"

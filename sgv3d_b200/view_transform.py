@@ -22,7 +22,7 @@ from torch.autograd import Function
 
 from . import _native as N
 
-__all__ = ["camera_matrices", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat",
+__all__ = ["camera_matrices", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat", "LiftSplatGraph",
            "build_frustum", "default_arith"]
 
 _DEFAULT_ARITH = N.ARITH_PAIR
@@ -409,3 +409,44 @@ class LiftSplat(nn.Module):
         plan = self.make_plan(mats_dict, sweep_index, int(tran_feat.shape[1]))
         # height softmax (bsm_lss_fpn.py:523) fused into the kernels
         return lift_splat(height_logits.float(), tran_feat.float(), plan, logits=True)
+
+
+class LiftSplatGraph:
+    """CUDA-graph replay of ``LiftSplat.forward_single_sweep`` for a serving loop with fixed shapes.
+
+    The whole per-step sequence -- the reference's per-camera 4x4 products (lss_fpn.py:361,367,392), the
+    plan kernels and the forward kernels -- is captured once and re-launched with a single
+    ``cudaGraphLaunch``: the ~25 small launches of a step otherwise cost more host time than the GPU
+    needs to run them.  Inference only (no autograd).  The captured graph reads the tensors handed to
+    the constructor (``height_feature`` and every entry of ``mats_dict``); ``__call__`` optionally
+    copies new values into them first, and returns the (B, C, Y, X) BEV map, which is overwritten by
+    the next call.  Geometry is recomputed on every replay, so the calibration may change per call.
+    """
+
+    def __init__(self, module: LiftSplat, height_feature: torch.Tensor, mats_dict, sweep_index: int = 0,
+                 warmup: int = 2):
+        if not height_feature.is_cuda:
+            raise RuntimeError("sgv3d_b200 runs on CUDA tensors only (no CPU fallback)")
+        self.module, self.sweep_index = module, sweep_index
+        self.height_feature = height_feature
+        self.mats_dict = mats_dict
+        self.device = height_feature.device
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):   # lazy initialisation (cuBLAS handles, smem attributes) before capture
+                module.forward_single_sweep(height_feature, mats_dict, sweep_index)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.bev = module.forward_single_sweep(height_feature, mats_dict, sweep_index)
+
+    def __call__(self, height_feature: Optional[torch.Tensor] = None, mats_dict=None) -> torch.Tensor:
+        if height_feature is not None and height_feature is not self.height_feature:
+            self.height_feature.copy_(height_feature, non_blocking=True)
+        if mats_dict is not None and mats_dict is not self.mats_dict:
+            for k, v in mats_dict.items():
+                if v is not None and self.mats_dict.get(k) is not None:
+                    self.mats_dict[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.bev
