@@ -43,9 +43,9 @@ namespace {
 
 constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
 
-// Sorted (voxel-major) entry: BYTE offset of the pixel's context row inside the frame's channels-last
-// copy (a multiple of 64) OR-ed with the voxel's index inside its 64-voxel reduce tile (written by the
-// plan), and the run weight (written by the forward weights pass).
+// Sorted (voxel-major) entry.  In the plan (global memory): frame-local pixel row (n*P + p) << 6 | the
+// voxel's index inside its 64-voxel reduce tile, and -- in the bits of `w` -- the ELL slot of the run.
+// Staged by the reduce kernel: same `off`, and the run weight gathered through that slot.
 struct __align__(8) Entry {
   unsigned off;
   float w;
@@ -74,7 +74,7 @@ struct __align__(8) BucketEnt {
 };
 
 struct Workspace {
-  int *run_cnt, *run_vox, *run_d, *run_dst, *hist, *tile_ptr, *row_ptr, *chunk_done;
+  int *run_cnt, *run_vox, *run_d, *hist, *tile_ptr, *row_ptr, *chunk_done;
   BucketEnt *bucket;
   Entry *vm_ent;  // sorted (row offset, weight) pairs
   float *w_pm, *gw_pm, *gT, *gctxT;
@@ -83,9 +83,10 @@ struct Workspace {
 };
 
 // Row layout by channel count: a G-lane group owns a whole channels-last row, NV 4-element vectors per
-// lane (Cpad = 4*G*NV, a multiple of 32 elements so that no 128-byte group access straddles a line).
+// lane (Cpad = 4*G*NV = 16*G*NV bytes in fp32: rows start on 64-byte boundaries, no padding at C = 80).
 void pick_row_cfg(int C, int *G, int *NV) {
-  if (C <= 128) { *G = 8; *NV = ceil_div(C, 32); }
+  if (C <= 96) { *G = 4; *NV = ceil_div(C, 16); }
+  else if (C <= 192) { *G = 8; *NV = ceil_div(C, 32); }
   else { *G = 16; *NV = ceil_div(C, 64); }
 }
 
@@ -110,7 +111,7 @@ Dims make_dims(const sgv3d_lift_splat_desc *d) {
   return m;
 }
 
-RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 8 ? 3 : 4, m.Cpad}; }
+RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 4 ? 2 : (m.G == 8 ? 3 : 4), m.Cpad}; }
 
 Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   Workspace w;
@@ -120,7 +121,6 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   w.run_cnt = c.take<int>(B * m.nchunks * kChunk);
   w.run_vox = c.take<int>(slots);
   w.run_d = c.take<int>(slots);
-  w.run_dst = c.take<int>(slots);
   w.hist = c.take<int>(B * m.nchunks * m.ntiles);
   w.tile_ptr = c.take<int>(B * (m.ntiles + 1));
   w.bucket = reinterpret_cast<BucketEnt *>(c.take<int2>(slots));
@@ -429,18 +429,15 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// PLAN 4/4: per tile, stable counting sort of the bucket by voxel-in-tile (6 bits).  Emits, per
-// sorted position, the context-row offset of the run's pixel OR-ed with the voxel-in-tile index, the
-// inverse permutation (ELL slot -> sorted position) that the forward weights pass scatters through,
-// and the CSR offsets of the tile's 64 voxels.  grid (ntiles, B), 128 threads; warp w owns the w-th
+// PLAN 4/4: per tile, stable counting sort of the bucket by voxel-in-tile (6 bits): the sorted entries
+// (pixel row | voxel-in-tile, ELL slot of the run) and the CSR offsets of the tile's 64 voxels.  grid (ntiles, B), 128 threads; warp w owns the w-th
 // quarter of the bucket (contiguous => the canonical order is kept).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinWarps = 4;
 
 __global__ void __launch_bounds__(kFinWarps * 32)
-ls_finish_tiles_kernel(Dims m, unsigned row_bytes, const int *__restrict__ tile_ptr,
-                       const BucketEnt *__restrict__ bucket, Entry *__restrict__ vm_ent,
-                       int *__restrict__ run_dst, int *__restrict__ row_ptr) {
+ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt *__restrict__ bucket,
+                       BucketEnt *__restrict__ vm_ent, int *__restrict__ row_ptr) {
   __shared__ int s_cnt[kFinWarps][64];
   const int b = blockIdx.y, tile = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -494,8 +491,7 @@ ls_finish_tiles_kernel(Dims m, unsigned row_bytes, const int *__restrict__ tile_
   }
   __syncthreads();
   const unsigned lt = lanemask_lt();
-  Entry *ve = vm_ent + (size_t)b * m.cap;
-  int *rd = run_dst + (size_t)b * m.cap;
+  BucketEnt *ve = vm_ent + (size_t)b * m.cap;
   for (int i0 = wb; i0 < we; i0 += 32) {
     const int i = i0 + lane;
     const bool valid = i < we;
@@ -513,11 +509,7 @@ ls_finish_tiles_kernel(Dims m, unsigned row_bytes, const int *__restrict__ tile_
       my[dig] = base + __popc(peers);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) {
-      const int pos = base + rank;
-      ve[pos].off = (e.key >> 6) * row_bytes | (e.key & 63u);
-      rd[e.slot] = pos;
-    }
+    if (valid) ve[base + rank] = e;
     __syncwarp();
   }
 }
@@ -558,32 +550,44 @@ __device__ __forceinline__ void stage_columns(float *col, const float *__restric
 // Softmax over D of this thread's staged column (torch.softmax within fp32 rounding:
 // exp(x - max) / sum).  Leaves the un-normalised exponentials in col and returns 1 / sum, so the
 // normalisation costs one multiply per run / per output instead of a pass over the column.
+// Four independent max / sum chains (fixed interleaving => still a deterministic order).
 __device__ __forceinline__ float softmax_column(float *col, int D, int t) {
-  float mx = -INFINITY;
-#pragma unroll 4
-  for (int d = 0; d < D; ++d) mx = fmaxf(mx, col[d * kChunk + t]);
-  float sum = 0.0f;
-#pragma unroll 4
-  for (int d = 0; d < D; ++d) {
-    const float e = expf(__fsub_rn(col[d * kChunk + t], mx));
-    col[d * kChunk + t] = e;
-    sum = __fadd_rn(sum, e);
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int d = 0;
+  for (; d + 4 <= D; d += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mx[k] = fmaxf(mx[k], col[(d + k) * kChunk + t]);
   }
-  return __fdiv_rn(1.0f, sum);
+  for (; d < D; ++d) mx[0] = fmaxf(mx[0], col[d * kChunk + t]);
+  const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  d = 0;
+  for (; d + 4 <= D; d += 4) {
+    float e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = expf(__fsub_rn(col[(d + k) * kChunk + t], m));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      col[(d + k) * kChunk + t] = e[k];
+      s[k] = __fadd_rn(s[k], e[k]);
+    }
+  }
+  for (; d < D; ++d) {
+    const float e = expf(__fsub_rn(col[d * kChunk + t], m));
+    col[d * kChunk + t] = e;
+    s[0] = __fadd_rn(s[0], e);
+  }
+  return __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3])));
 }
 
 // ---------------------------------------------------------------------------------------------
-// FORWARD / BACKWARD: run weights  w = sum_{d in run} p[d, pixel]  (ascending d, fixed order).
-// DST_SORTED: write to the run's voxel-major slot (forward) else pixel-major ELL (backward).
+// FORWARD / BACKWARD: run weights  w = sum_{d in run} p[d, pixel]  (ascending d, fixed order), written
+// pixel-major (ELL slot of the run; coalesced).  The forward reduce gathers them through the slot
+// index its sorted entries carry.
 // ---------------------------------------------------------------------------------------------
-template <bool DST_SORTED>
-__global__ void __launch_bounds__(kChunk)
-ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
-                  const int *__restrict__ run_cnt, const int *__restrict__ run_d,
-                  const int *__restrict__ run_dst, float *__restrict__ w_pm_out,
-                  Entry *__restrict__ vm_ent_out) {
-  extern __shared__ float col[];
-  const int b = blockIdx.y, chunk = blockIdx.x;
+__device__ __forceinline__ void weights_role(const Dims &m, const float *__restrict__ height, int vec16,
+                                             const int *__restrict__ run_cnt, const int *__restrict__ run_d,
+                                             float *__restrict__ w_pm_out, float *col, int b, int chunk) {
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;
   const int t = threadIdx.x;
@@ -595,15 +599,11 @@ ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
   const float scale = m.logits ? softmax_column(col, m.D, t) : 1.0f;
   // batch the (strided) run descriptors 4 at a time
   for (int r0 = 0; r0 < cnt; r0 += 4) {
-    int packed[4], dst[4];
+    int packed[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      packed[u] = 0; dst[u] = 0;
-      if (r0 + u < cnt) {
-        const size_t s = ell_slot(frame_chunk, m.D, r0 + u, t);
-        packed[u] = run_d[s];
-        if (DST_SORTED) dst[u] = run_dst[s];
-      }
+      packed[u] = 0;
+      if (r0 + u < cnt) packed[u] = run_d[ell_slot(frame_chunk, m.D, r0 + u, t)];
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -611,20 +611,64 @@ ls_weights_kernel(Dims m, const float *__restrict__ height, int vec16,
         const int d0 = packed[u] & 0xffff, d1 = packed[u] >> 16;
         float acc = 0.0f;
         for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-        const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
-        if (DST_SORTED) vm_ent_out[(size_t)b * m.cap + dst[u]].w = wgt;
-        else w_pm_out[ell_slot(frame_chunk, m.D, r0 + u, t)] = wgt;
+        w_pm_out[ell_slot(frame_chunk, m.D, r0 + u, t)] = m.logits ? __fmul_rn(acc, scale) : acc;
       }
     }
   }
 }
 
+// Context rows: the C x 128 NCHW block of one pixel chunk -> 128 channels-last rows (permuted channel
+// order, transpose.cuh: RowPerm).  Reads are coalesced 512-byte channel rows (cp.async, all in flight at
+// once), writes are coalesced 128-byte pieces of the pixel rows; the smem tile is [C][129] (conflict-free
+// both ways: consecutive pixels on the way in, 32 distinct channels of one pixel on the way out).
+template <typename CT>
+__device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__restrict__ context,
+                                                  CT *__restrict__ ctxT, RowPerm perm, float *smem, int b,
+                                                  int chunk) {
+  constexpr int kLd = kChunk + 1;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int p0 = ci * kChunk;
+  const int npx = min(kChunk, m.P - p0);
+  const CT *src = context + (size_t)(b * m.Nc + n) * m.cs + p0;
+  if (sizeof(CT) == 4) {
+    if (t < npx)
+      for (int c = 0; c < m.C; ++c)
+        cp_async_4(smem + c * kLd + t, reinterpret_cast<const float *>(src) + (size_t)c * m.P + t);
+    cp_async_wait_all();
+  } else {
+    if (t < npx)
+      for (int c = 0; c < m.C; ++c) smem[c * kLd + t] = to_f32<CT>(src[(size_t)c * m.P + t]);
+  }
+  __syncthreads();
+  CT *dst = ctxT + ((size_t)(b * m.Nc + n) * m.P + p0) * m.Cpad;
+  // lane <-> element of the row (3 pieces of 32 elements cover Cpad <= 96; loop for wider rows)
+  for (int e0 = 0; e0 < m.Cpad; e0 += 32) {
+    const int e = e0 + lane;
+    const int c = e < m.Cpad ? perm.chan(e) : m.C;
+    const bool live = e < m.Cpad;
+    const bool real = c < m.C;
+    for (int px = wid; px < npx; px += kChunk / 32) {
+      const float v = real ? smem[c * kLd + px] : 0.0f;
+      if (live) dst[(size_t)px * m.Cpad + e] = from_f32<CT>(v);
+    }
+  }
+}
+
+// One launch, two kinds of CTA (blockIdx.z): run weights of a pixel chunk (ALU / latency bound) and
+// channels-last context rows of a pixel chunk (bandwidth bound) -- they overlap on every SM.
+template <typename CT>
+__global__ void __launch_bounds__(kChunk)
+ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
+                    const int *__restrict__ run_d, float *__restrict__ w_pm_out,
+                    const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm) {
+  extern __shared__ float lift_smem[];
+  if (blockIdx.z == 0) weights_role(m, height, vec16, run_cnt, run_d, w_pm_out, lift_smem, blockIdx.y, blockIdx.x);
+  else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------
-// FORWARD: per-voxel weighted gather of context rows.
-// grid (ceil(V/32), B), 256 threads.  CTA = 32 consecutive voxels (one 128-byte strip of every
-// output channel plane).  The strip's CSR offsets and its (pixel, weight) entries are staged in
-// shared memory first (coalesced, one round trip), then warp w accumulates voxels 4w..4w+3 with
-// 8 independent 128-bit row loads in flight; lanes own 4-channel slices of a row.
+// FORWARD: per-voxel weighted gather of context rows (sparse voxel x pixel times dense pixel x C).
 // ---------------------------------------------------------------------------------------------
 template <typename CT>
 struct RowLoad;
@@ -647,8 +691,7 @@ struct RowLoad<__nv_bfloat16> {
 
 // ---- reduce: tile geometry ----------------------------------------------------------------------
 constexpr int kTileV = 64;     // voxels per reduce CTA: two 32-voxel boxes = 2 x 128-byte rows per channel
-constexpr int kRedWarps = 8;   // warps per reduce CTA
-constexpr int kStageE = 2048;  // entries staged in shared memory (larger tiles read them from global)
+constexpr int kStageE = 1536;  // entries staged in shared memory (larger tiles read them from global)
 static_assert(kTileV == 64, "Entry::off carries the voxel-in-tile index in its low 6 bits");
 
 // 4-element row vector widened to fp32 (byte address).
@@ -686,107 +729,152 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
 
 // Byte offset of the 16-byte chunk j (4 voxels) of channel row r inside one 32-voxel box of the
 // tile: 128-byte rows, chunk index XOR-ed with (row & 7) -- the TMA SWIZZLE_128B pattern -- so that
-// lanes holding rows r, r+1, .. r+7 of the same voxel column hit eight different bank groups.
+// lanes holding different rows of the same voxel column hit different bank groups.
 __device__ __forceinline__ int tile_chunk(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
-// One stream = one G-lane group walking a contiguous slice [j, jend) of the tile's sorted entries.
-// Lane l owns channels l + G*t (t < 4*NV) of every gathered row; a voxel's sum is complete when the
-// voxel index carried by the entries changes, and is then written to column vt of the tile.
-template <typename CT, int G, int NV, bool STAGED>
-__device__ __forceinline__ void run_stream(const unsigned char *__restrict__ lane_rows,
-                                           const Entry *__restrict__ ent, int j, int jend,
-                                           unsigned tile_lane /*smem addr of row l, chunk 0*/, int l7,
-                                           unsigned box_bytes) {
-  float acc[NV][4];
+// Per-lane accumulator of one stream: lane l of a G-lane group owns channels l + G*j, j < 4*NV, of every
+// gathered row (vector k, element e <-> j = 4k + e: the permuted channels-last row layout, transpose.cuh).
+template <int G, int NV>
+struct StreamAcc {
+  float a[NV][4];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int k = 0; k < NV; ++k)
+    for (int k = 0; k < NV; ++k)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
-  int cur = -1;
-  auto flush = [&]() {
-    const unsigned a = tile_lane + (cur >> 5) * box_bytes + (((((unsigned)cur >> 2) & 7u) ^ (unsigned)l7) << 4) +
-                       (((unsigned)cur & 3u) << 2);
+      for (int e = 0; e < 4; ++e) a[k][e] = 0.0f;
+  }
+  // write the sums to voxel column vt of the swizzled [channel][voxel] tile, then clear
+  __device__ __forceinline__ void flush_tile(unsigned tile_lane /*smem addr of row l, chunk 0*/, int l,
+                                             unsigned box_bytes, int vt) {
+    // row r = l + G*j: (r & 7) = l & 7 for G >= 8;  for G = 4 it is (l + 4*(j & 1)): bit 2 toggles with j
+    const unsigned chunk = (((unsigned)vt >> 2) & 7u) ^ ((unsigned)l & 7u);
+    const unsigned base = tile_lane + ((unsigned)vt >> 5) * box_bytes + (((unsigned)vt & 3u) << 2);
+    const unsigned a0 = base + (chunk << 4), a1 = base + ((chunk ^ 4u) << 4);
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        sts_f32(a + (4 * k + e) * G * 128, acc[k][e]);
-        acc[k][e] = 0.0f;
+        const int j = 4 * k + e;
+        sts_f32(((G == 4 && (j & 1)) ? a1 : a0) + j * G * 128, a[k][e]);
+        a[k][e] = 0.0f;
       }
-  };
-  constexpr int U = 2;
-  // the groups of a warp iterate in lockstep: uniform trip count = the longest slice
-  const int len = jend - j;
-  int iters = (len + U - 1) / U;
+  }
+  // partial sum of a voxel that an earlier stream started: parked per stream, added by that stream later
+  __device__ __forceinline__ void store_head(float *head /*[4*G*NV] of this stream*/, int l) {
 #pragma unroll
-  for (int o = G; o < 32; o <<= 1) iters = max(iters, __shfl_xor_sync(0xffffffffu, iters, o));
-#pragma unroll 1
-  for (int it = 0; it < iters; ++it, j += U) {
-    Entry en[U];
-    bool ok[U];
-    float r[U][NV][4];
+    for (int k = 0; k < NV; ++k) {
+      *reinterpret_cast<float4 *>(head + 4 * (k * G + l)) = make_float4(a[k][0], a[k][1], a[k][2], a[k][3]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      ok[u] = j + u < jend;
-      if (ok[u]) {
-        if (STAGED) en[u] = ent[j + u];
-        else {
-          const uint2 t = __ldg(reinterpret_cast<const uint2 *>(ent + j + u));
-          en[u].off = t.x; en[u].w = __uint_as_float(t.y);
-        }
-        const unsigned char *row = lane_rows + (en[u].off & ~63u);
-#pragma unroll
-        for (int k = 0; k < NV; ++k) RowLd<CT>::vec(row + k * G * 4 * sizeof(CT), r[u][k]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (ok[u]) {
-        const int vt = (int)(en[u].off & 63u);
-        if (vt != cur) {
-          if (cur >= 0) flush();
-          cur = vt;
-        }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          fma2(acc[k][0], acc[k][1], en[u].w, r[u][k][0], r[u][k][1]);
-          fma2(acc[k][2], acc[k][3], en[u].w, r[u][k][2], r[u][k][3]);
-        }
-      }
+      for (int e = 0; e < 4; ++e) a[k][e] = 0.0f;
     }
   }
-  if (cur >= 0) flush();
+  __device__ __forceinline__ void add_head(const float *head, int l) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 h = *reinterpret_cast<const float4 *>(head + 4 * (k * G + l));
+      a[k][0] = __fadd_rn(a[k][0], h.x); a[k][1] = __fadd_rn(a[k][1], h.y);
+      a[k][2] = __fadd_rn(a[k][2], h.z); a[k][3] = __fadd_rn(a[k][3], h.w);
+    }
+  }
+};
+
+// One stream = one G-lane group walking the slice [j0, j1) of the tile's sorted entries, two entries in
+// flight.  STAGED: entries (row | voxel, weight) come from shared memory; otherwise (huge tiles) from the
+// plan in global memory, the weight gathered through the entry's slot index.
+template <typename CT, int G, int NV, bool STAGED>
+__device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, bool &head,
+                                            const Entry *__restrict__ ent, const float *__restrict__ wf,
+                                            int j0, int j1, const int *s_rp,
+                                            const unsigned char *__restrict__ lane_rows, unsigned tile_lane,
+                                            float *my_head, int l, unsigned box_bytes) {
+  constexpr unsigned kRowBytes = 4 * G * NV * sizeof(CT);
+  auto load_entry = [&](int j, Entry &en) {
+    if (STAGED) en = ent[j];
+    else {
+      const uint2 t = __ldg(reinterpret_cast<const uint2 *>(ent + j));
+      en.off = t.x;
+      en.w = __ldg(wf + t.y);
+    }
+  };
+  auto load_row = [&](const Entry &en, float (&r)[NV][4]) {
+    const unsigned char *row = lane_rows + (size_t)(en.off >> 6) * kRowBytes;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) RowLd<CT>::vec(row + k * G * 4 * sizeof(CT), r[k]);
+  };
+  auto accumulate = [&](const Entry &en, const float (&r)[NV][4]) {
+    const int vt = (int)(en.off & 63u);
+    if (vt != cur) {
+      if (cur >= 0) {
+        if (head) acc.store_head(my_head, l);
+        else acc.flush_tile(tile_lane, l, box_bytes, cur);
+        head = false;
+      }
+      cur = vt;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      fma2(acc.a[k][0], acc.a[k][1], en.w, r[k][0], r[k][1]);
+      fma2(acc.a[k][2], acc.a[k][3], en.w, r[k][2], r[k][3]);
+    }
+  };
+  if (j0 >= j1) return;
+  {
+    Entry e0;
+    load_entry(j0, e0);
+    head = j0 > s_rp[e0.off & 63u];
+  }
+  int j = j0;
+#pragma unroll 1
+  for (; j + 2 <= j1; j += 2) {
+    Entry ea, eb;
+    float ra[NV][4], rb[NV][4];
+    load_entry(j, ea);
+    load_entry(j + 1, eb);
+    load_row(ea, ra);
+    load_row(eb, rb);
+    accumulate(ea, ra);
+    accumulate(eb, rb);
+  }
+  if (j < j1) {
+    Entry ea;
+    float ra[NV][4];
+    load_entry(j, ea);
+    load_row(ea, ra);
+    accumulate(ea, ra);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// FORWARD: per-voxel weighted gather of context rows (sparse voxel x pixel times dense pixel x C).
-// grid (ceil(V / 64), B), 256 threads.  CTA = tile of 64 consecutive voxels:
-//   1. the tile's CSR offsets and its sorted (row offset | voxel, weight) entries are staged in shared
-//      memory with coalesced loads (one round trip for the whole tile); the [channel][voxel] tile is zeroed;
-//   2. the tile's entry list is cut at voxel boundaries into 32 (G = 8) or 16 (G = 16) slices of near-equal
-//      length, one per G-lane group ("stream"): perfectly regular work whatever the points-per-voxel
-//      distribution looks like.  A group owns whole context rows (NV 128-bit loads per lane and entry, 4
-//      entries per warp instruction when G = 8), packed FFMA2, 2 entries per stream in flight; every
-//      voxel is summed by exactly one stream in sorted entry order => deterministic, no atomics;
-//   3. finished voxel sums go to a swizzled [channel][voxel] tile (conflict-free for G = 8), and the
-//      tile leaves as 128-byte row segments of the NCHW planes (fully coalesced, every output byte
-//      written exactly once).
+// grid (ceil(V / 64), B), 32 * NSTR * G / 32 threads.  CTA = tile of 64 consecutive voxels:
+//   1. the tile's CSR offsets and its sorted entries are staged in shared memory with coalesced loads;
+//      the run weights are gathered through the entries' slot index on the way (one round trip for the
+//      whole tile); the [channel][voxel] tile is zeroed;
+//   2. the tile's entry list is cut into NSTR slices of EQUAL length (+-1), one per G-lane group
+//      ("stream"): perfectly regular work whatever the points-per-voxel distribution looks like.  A group
+//      owns whole context rows (NV 128-bit loads per lane and entry), packed FFMA2, 2 entries per stream
+//      in flight.  A voxel cut by a slice boundary is summed in slice order: every later slice parks its
+//      partial ("head") in shared memory, and the slice that started the voxel adds the heads in order
+//      after a barrier => one fixed summation order per voxel, no atomics, bitwise reproducible;
+//   3. finished voxel sums go to a swizzled [channel][voxel] tile, and the tile leaves as 128-byte row
+//      segments of the NCHW planes (fully coalesced, every output byte written exactly once).
 // ---------------------------------------------------------------------------------------------
-template <typename CT, int G, int NV>
-__global__ void __launch_bounds__(kRedWarps * 32)
+template <typename CT, int G, int NV, int NSTR>
+__global__ void __launch_bounds__(NSTR * G)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
-                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out) {
+                 const Entry *__restrict__ vm_ent, const float *__restrict__ w_pm,
+                 float *__restrict__ bev, int vec_out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kThreads = NSTR * G;
   constexpr int kRows = 4 * G * NV;                  // = Cpad rows (rows >= C are scratch)
   constexpr unsigned kBoxBytes = kRows * 128;
-  unsigned char *tile = smem_raw;                                       // 2 boxes x kRows x 128 B
-  Entry *s_ent = reinterpret_cast<Entry *>(smem_raw + 2 * kBoxBytes);   // kStageE entries
+  unsigned char *tile = smem_raw;                                          // 2 boxes x kRows x 128 B
+  float *s_head = reinterpret_cast<float *>(smem_raw + 2 * kBoxBytes);     // NSTR x kRows partial sums
+  Entry *s_ent = reinterpret_cast<Entry *>(s_head + NSTR * kRows);         // kStageE entries
   __shared__ int s_rp[kTileV + 1];
-  constexpr int SPW = 32 / G;              // streams per warp
-  constexpr int NSTR = kRedWarps * SPW;    // streams per CTA
   const int b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int sub = lane / G, l = lane & (G - 1);
+  const int tid = threadIdx.x;
+  const int l = tid & (G - 1);
+  const int s = tid / G;  // stream index: consecutive streams sit in one warp
   const int v0 = blockIdx.x * kTileV;
   const int nv = min(kTileV, m.V - v0);
   const int *rp = row_ptr + (size_t)b * (m.V + 1) + v0;
@@ -795,17 +883,19 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   const int tile_lo = s_rp[0], tile_hi = s_rp[kTileV];
   float *out = bev + (size_t)b * m.C * m.V + v0;
 
-  // thread <-> (channel row c0 + 16*i, 16-byte chunk q) of the tile for the copy-out loops
+  // thread <-> (channel row c0 + kThreads/16 * i, 16-byte chunk q) of the tile for the copy-out loops
+  constexpr int kRowStep = kThreads / 16;
+  static_assert(kRowStep % 8 == 0, "copy-out relies on (row & 7) being loop invariant");
   const int q = tid & 15, c0 = tid >> 4;
   if (tile_hi == tile_lo) {  // no point falls into this tile: zero fill
     if (vec_out) {
       if (4 * q < nv) {
         float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)c0 * m.V) + q;
-        const size_t step = (size_t)4 * m.V;  // 16 channel rows, in float4 units
-        for (int c = c0; c < m.C; c += 16, o4 += step) stg_stream_f4(o4, make_float4(0.f, 0.f, 0.f, 0.f));
+        const size_t step = (size_t)(kRowStep / 4) * m.V;  // kRowStep channel rows, in float4 units
+        for (int c = c0; c < m.C; c += kRowStep, o4 += step) stg_stream_f4(o4, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     } else {
-      for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
+      for (int i = tid; i < m.C * kTileV; i += kThreads) {
         const int c = i >> 6, j = i & 63;
         if (j < nv) stg_stream_f1(out + (size_t)c * m.V + j, 0.0f);
       }
@@ -816,50 +906,65 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   const int n_t = tile_hi - tile_lo;
   const bool staged = n_t <= kStageE;
   const Entry *ent = vm_ent + (size_t)b * m.cap;
-  if (staged)
-    for (int i = tid; i < n_t; i += kRedWarps * 32) s_ent[i] = ent[tile_lo + i];
-  for (int i = tid; i < 2 * (int)kBoxBytes / 16; i += kRedWarps * 32)
-    reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  // stream s owns the voxels [vb(s), vb(s+1)),  vb(k) = #{v in [0, 64] : rp[v] < tile_lo + k * n_t / NSTR}
-  // (rp is non-decreasing; vb(0) = 0, vb(NSTR) = 64): slices of near-equal entry counts cut at voxel
-  // boundaries.  Counted with two ballots over the 65 offsets held one / two per lane.
-  const int rp_a = s_rp[lane], rp_b = s_rp[32 + lane];
-  int vs = 0, ve = 0;
-#pragma unroll
-  for (int ss = 0; ss <= SPW; ++ss) {
-    const int k = wid * SPW + ss;
-    const int target = tile_lo + (int)(((long long)n_t * k) / NSTR);
-    const int vb = __popc(__ballot_sync(0xffffffffu, rp_a < target)) + __popc(__ballot_sync(0xffffffffu, rp_b < target));
-    if (ss == sub) vs = vb;
-    if (ss == sub + 1) ve = vb;
+  const float *wf = w_pm + (size_t)b * m.cap;
+  if (staged) {
+    for (int i = tid; i < n_t; i += kThreads) {
+      const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ent + tile_lo + i));
+      Entry o;
+      o.off = e.x;
+      o.w = __ldg(wf + e.y);
+      s_ent[i] = o;
+    }
   }
-  int jb[2];
-  jb[0] = s_rp[vs];
-  jb[1] = s_rp[ve];
+  for (int i = tid; i < 2 * (int)kBoxBytes / 16; i += kThreads)
+    reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
+  // stream s owns the entries [j0, j1) of the tile: equal slices
+  const int E = (n_t + NSTR - 1) / NSTR;
+  const int j0 = tile_lo + min(s * E, n_t), j1 = tile_lo + min((s + 1) * E, n_t);
   const unsigned char *lane_rows = reinterpret_cast<const unsigned char *>(ctxT) +
                                    ((size_t)b * m.Nc * m.P * m.Cpad + 4 * l) * sizeof(CT);
   const unsigned tile_lane = (unsigned)__cvta_generic_to_shared(tile) + l * 128;
+  float *my_head = s_head + s * kRows;
+
+  StreamAcc<G, NV> acc;
+  acc.clear();
+  int cur = -1;         // voxel (in tile) being accumulated
+  bool head = false;    // the segment being accumulated continues a voxel started by an earlier stream
   if (staged)
-    run_stream<CT, G, NV, true>(lane_rows, s_ent - tile_lo, jb[0], jb[1], tile_lane, l & 7, kBoxBytes);
+    stream_loop<CT, G, NV, true>(acc, cur, head, s_ent - tile_lo, nullptr, j0, j1, s_rp, lane_rows, tile_lane,
+                                 my_head, l, kBoxBytes);
   else
-    run_stream<CT, G, NV, false>(lane_rows, ent, jb[0], jb[1], tile_lane, l & 7, kBoxBytes);
+    stream_loop<CT, G, NV, false>(acc, cur, head, ent, wf, j0, j1, s_rp, lane_rows, tile_lane, my_head, l,
+                                  kBoxBytes);
+  // the last segment of the slice: complete iff the slice ends on the voxel's last entry
+  bool tail = false;
+  if (cur >= 0) {
+    if (head) acc.store_head(my_head, l);                 // the whole slice lies inside one earlier voxel
+    else if (s_rp[cur + 1] == j1) acc.flush_tile(tile_lane, l, kBoxBytes, cur);
+    else tail = true;                                      // later slices continue this voxel
+  }
+  __syncthreads();
+  if (tail) {
+    const int vend = s_rp[cur + 1];
+    for (int k = s + 1; k < NSTR && tile_lo + k * E < vend; ++k) acc.add_head(s_head + k * kRows, l);
+    acc.flush_tile(tile_lane, l, kBoxBytes, cur);
+  }
   __syncthreads();
 
   // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line.
-  // Rows advance by 16 per step, so (row & 7) and with it the swizzled chunk position never change.
+  // Rows advance by a multiple of 8 per step, so (row & 7) and with it the swizzled chunk position never change.
   if (vec_out) {
     if (4 * q < nv) {
       const unsigned char *t4 = tile + (q >> 3) * kBoxBytes + tile_chunk(c0, q & 7);
       float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)c0 * m.V) + q;
-      const size_t step = (size_t)4 * m.V;
-      for (int c = c0; c < m.C; c += 16, o4 += step, t4 += 16 * 128)
+      const size_t step = (size_t)(kRowStep / 4) * m.V;
+      for (int c = c0; c < m.C; c += kRowStep, o4 += step, t4 += kRowStep * 128)
         stg_stream_f4(o4, *reinterpret_cast<const float4 *>(t4));
     }
   } else {
-    for (int i = tid; i < m.C * kTileV; i += kRedWarps * 32) {
+    for (int i = tid; i < m.C * kTileV; i += kThreads) {
       const int c = i >> 6, j = i & 63, qq = j >> 2;
       if (j < nv)
         stg_stream_f1(out + (size_t)c * m.V + j,
@@ -1058,36 +1163,44 @@ bool columns_vec16(const float *base, long long batch_stride, int P) {
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
+  if (bytes > 40 * 1024)  // dynamic + static shared memory beyond 48 KB needs the opt-in
     SGV3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return SGV3D_OK;
 }
 
-template <typename CT, int G, int NV>
+template <typename CT, int G, int NV, int NSTR>
 int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
   dim3 grid(ceil_div(m.V, kTileV), m.B);
-  const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(Entry) * kStageE;
-  if (int rc = set_smem(ls_reduce_kernel<CT, G, NV>, smem)) return rc;
+  const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * kStageE;
+  if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR>, smem)) return rc;
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
-  ls_reduce_kernel<CT, G, NV><<<grid, kRedWarps * 32, smem, s>>>(
-      m, static_cast<const CT *>(w.ctxT), w.row_ptr, w.vm_ent, bev, vec_out);
+  ls_reduce_kernel<CT, G, NV, NSTR><<<grid, NSTR * G, smem, s>>>(
+      m, static_cast<const CT *>(w.ctxT), w.row_ptr, w.vm_ent, w.w_pm, bev, vec_out);
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
 }
 
 template <typename CT>
 int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
-  if (m.G == 8) {
+  if (m.G == 4) {
     switch (m.NV) {
-      case 1: return launch_reduce_cfg<CT, 8, 1>(m, w, bev, s);
-      case 2: return launch_reduce_cfg<CT, 8, 2>(m, w, bev, s);
-      case 3: return launch_reduce_cfg<CT, 8, 3>(m, w, bev, s);
-      default: return launch_reduce_cfg<CT, 8, 4>(m, w, bev, s);
+      case 1: return launch_reduce_cfg<CT, 4, 1, 32>(m, w, bev, s);
+      case 2: return launch_reduce_cfg<CT, 4, 2, 32>(m, w, bev, s);
+      case 3: return launch_reduce_cfg<CT, 4, 3, 32>(m, w, bev, s);
+      case 4: return launch_reduce_cfg<CT, 4, 4, 32>(m, w, bev, s);
+      case 5: return launch_reduce_cfg<CT, 4, 5, 32>(m, w, bev, s);
+      default: return launch_reduce_cfg<CT, 4, 6, 32>(m, w, bev, s);
     }
   }
-  if (m.NV <= 3) return launch_reduce_cfg<CT, 16, 3>(m, w, bev, s);
-  return launch_reduce_cfg<CT, 16, 4>(m, w, bev, s);
+  if (m.G == 8) {
+    switch (m.NV) {
+      case 4: return launch_reduce_cfg<CT, 8, 4, 32>(m, w, bev, s);
+      case 5: return launch_reduce_cfg<CT, 8, 5, 32>(m, w, bev, s);
+      default: return launch_reduce_cfg<CT, 8, 6, 32>(m, w, bev, s);
+    }
+  }
+  return launch_reduce_cfg<CT, 16, 4, 16>(m, w, bev, s);
 }
 
 template <typename CT>
@@ -1104,29 +1217,25 @@ int launch_backward_gather(const Dims &m, const Workspace &w, int gpad, cudaStre
   return SGV3D_OK;
 }
 
-int transpose_context(const Dims &m, const Workspace &w, int ctx_dtype, const void *context,
-                      cudaStream_t s) {
-  const int batch = m.B * m.Nc;
-  if (ctx_dtype == SGV3D_DTYPE_BF16)
-    launch_transpose_pad<__nv_bfloat16, __nv_bfloat16, 1>(
-        static_cast<const __nv_bfloat16 *>(context), static_cast<__nv_bfloat16 *>(w.ctxT), batch, m.C,
-        m.P, m.P, (size_t)m.cs, m.Cpad, (size_t)m.P * m.Cpad, s, row_perm(m));
-  else
-    launch_transpose_pad<float, float, 1>(static_cast<const float *>(context), static_cast<float *>(w.ctxT),
-                                          batch, m.C, m.P, m.P, (size_t)m.cs, m.Cpad,
-                                          (size_t)m.P * m.Cpad, s, row_perm(m));
-  SGV3D_CHECK_LAUNCH("transpose_pad_kernel(context)");
-  return SGV3D_OK;
-}
-
-template <bool DST_SORTED>
-int launch_weights(const Dims &m, const Workspace &w, const float *height, cudaStream_t s) {
-  dim3 gc(m.nchunks, m.B);
-  const size_t smem = sizeof(float) * m.D * kChunk;
-  if (int rc = set_smem(ls_weights_kernel<DST_SORTED>, smem)) return rc;
-  ls_weights_kernel<DST_SORTED><<<gc, kChunk, smem, s>>>(m, height, columns_vec16(height, m.hs, m.P) ? 1 : 0,
-                                                        w.run_cnt, w.run_d, w.run_dst, w.w_pm, w.vm_ent);
-  SGV3D_CHECK_LAUNCH("ls_weights_kernel");
+// weights + context rows in one launch (forward and backward need both)
+int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const float *height, const void *context,
+                     cudaStream_t s) {
+  dim3 grid(m.nchunks, m.B, 2);
+  const size_t smem = sizeof(float) * (size_t)(m.D > m.C ? m.D * kChunk : m.C * (kChunk + 1));
+  const size_t smem2 = sizeof(float) * (size_t)kChunk * m.D > smem ? sizeof(float) * (size_t)kChunk * m.D : smem;
+  const int vec16 = columns_vec16(height, m.hs, m.P) ? 1 : 0;
+  if (ctx_dtype == SGV3D_DTYPE_BF16) {
+    if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16>, smem2)) return rc;
+    ls_lift_prep_kernel<__nv_bfloat16><<<grid, kChunk, smem2, s>>>(
+        m, height, vec16, w.run_cnt, w.run_d, w.w_pm, static_cast<const __nv_bfloat16 *>(context),
+        static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m));
+  } else {
+    if (int rc = set_smem(ls_lift_prep_kernel<float>, smem2)) return rc;
+    ls_lift_prep_kernel<float><<<grid, kChunk, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.w_pm,
+                                                          static_cast<const float *>(context),
+                                                          static_cast<float *>(w.ctxT), row_perm(m));
+  }
+  SGV3D_CHECK_LAUNCH("ls_lift_prep_kernel");
   return SGV3D_OK;
 }
 
@@ -1188,7 +1297,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   ls_scatter_tiles_kernel<<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
   SGV3D_CHECK_LAUNCH("ls_scatter_tiles_kernel");
   ls_finish_tiles_kernel<<<dim3(m.ntiles, m.B), kFinWarps * 32, 0, s>>>(
-      m, (unsigned)(m.Cpad * m.esize), w.tile_ptr, w.bucket, w.vm_ent, w.run_dst, w.row_ptr);
+      m, w.tile_ptr, w.bucket, reinterpret_cast<BucketEnt *>(w.vm_ent), w.row_ptr);
   SGV3D_CHECK_LAUNCH("ls_finish_tiles_kernel");
   return SGV3D_OK;
 }
@@ -1204,8 +1313,7 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
-  if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
-  if (int rc = launch_weights<true>(m, w, height, s)) return rc;
+  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, s)) return rc;
   if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
   return launch_reduce<float>(m, w, bev, s);
 }
@@ -1224,11 +1332,10 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   const int gpad = m.Cpad;  // gradient rows share the context rows' (permuted) channel layout
-  if (int rc = transpose_context(m, w, desc->ctx_dtype, context, s)) return rc;
+  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, s)) return rc;
   launch_transpose_pad<float, float, 1>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
                                         (size_t)m.V * gpad, s, row_perm(m));
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_bev)");
-  if (int rc = launch_weights<false>(m, w, height, s)) return rc;
   int rc = desc->ctx_dtype == SGV3D_DTYPE_BF16 ? launch_backward_gather<__nv_bfloat16>(m, w, gpad, s)
                                                 : launch_backward_gather<float>(m, w, gpad, s);
   if (rc) return rc;

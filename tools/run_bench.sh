@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -6; python bench.py --steps 20 --warmup 3 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; python - <<PY
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -25; python bench.py --steps 20 --warmup 3 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_tmp.json"))
 print("value",round(d["value"]),"ms/step",round(d["ms_per_step"],4),"e2e",round(d["e2e"]["value"]),"launches",d["gpu_launches"])
