@@ -43,9 +43,9 @@ namespace {
 
 constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
 
-// Sorted (voxel-major) entry.  In the plan (global memory): frame-local pixel row (n*P + p) << 6 | the
-// voxel's index inside its 64-voxel reduce tile, and -- in the bits of `w` -- the ELL slot of the run.
-// Staged by the reduce kernel: same `off`, and the run weight gathered through that slot.
+// Sorted (voxel-major) entry: frame-local pixel row (n*P + p) << 6 | the voxel's index inside its 64-voxel
+// reduce tile (written by the plan), and the run weight (written by the forward weights pass through
+// run_dst, the plan's ELL slot -> sorted position map).
 struct __align__(8) Entry {
   unsigned off;
   float w;
@@ -74,7 +74,7 @@ struct __align__(8) BucketEnt {
 };
 
 struct Workspace {
-  int *run_cnt, *run_vox, *run_d, *hist, *tile_ptr, *row_ptr, *chunk_done;
+  int *run_cnt, *run_vox, *run_d, *run_dst, *hist, *tile_ptr, *chunk_done;
   BucketEnt *bucket;
   Entry *vm_ent;  // sorted (row offset, weight) pairs
   float *w_pm, *gw_pm, *gT, *gctxT;
@@ -121,11 +121,11 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   w.run_cnt = c.take<int>(B * m.nchunks * kChunk);
   w.run_vox = c.take<int>(slots);
   w.run_d = c.take<int>(slots);
+  w.run_dst = c.take<int>(slots);
   w.hist = c.take<int>(B * m.nchunks * m.ntiles);
   w.tile_ptr = c.take<int>(B * (m.ntiles + 1));
   w.bucket = reinterpret_cast<BucketEnt *>(c.take<int2>(slots));
   w.vm_ent = reinterpret_cast<Entry *>(c.take<int2>(slots));
-  w.row_ptr = c.take<int>(B * (m.V + 1));
   w.w_pm = c.take<float>(slots);
   w.gw_pm = c.take<float>(slots);
   const size_t rows = B * m.Nc * m.P;
@@ -136,6 +136,24 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   w.gctxT = c.take<float>(rows * gpad);
   w.bytes = c.used();
   return w;
+}
+
+// ---- cp.async: global -> shared copies that do not pass through registers ------------------------
+__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
 
 __device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t) {
@@ -307,14 +325,51 @@ constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
 ls_scan_tiles_kernel(Dims m, int *__restrict__ hist, int *__restrict__ tile_ptr) {
   __shared__ int s_tot[kMaxTiles];
+  __shared__ int s_part[kMaxTiles];  // [group][bin] partial sums of one sweep (groups * width <= 1024 per sweep)
   __shared__ int s_warp[kScanThreads / 32];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   int *h = hist + (size_t)b * m.nchunks * m.ntiles;
-  for (int bin = t; bin < kMaxTiles; bin += kScanThreads) {
+  // `width` threads cover the bins of one sweep; the 1024 / width thread groups split the chunk axis
+  int width = 32;
+  while (width < m.ntiles && width < kScanThreads) width <<= 1;
+  const int groups = kScanThreads / width;
+  const int g = t / width, lb = t - g * width;
+  const int cpg = (m.nchunks + groups - 1) / groups;
+  const int c_lo = min(g * cpg, m.nchunks), c_hi = min(c_lo + cpg, m.nchunks);
+  for (int bin0 = 0; bin0 < kMaxTiles; bin0 += width) {
+    if (bin0 >= m.ntiles) {  // (block-uniform) tiles beyond the grid hold no runs
+      for (int i = bin0 + t; i < kMaxTiles; i += kScanThreads) s_tot[i] = 0;
+      break;
+    }
+    const int bin = bin0 + lb;
+    const bool live = bin < m.ntiles;
+    // sweep 1: this group's share of the bin's runs
+    int part = 0;
+    if (live) {
+      int c = c_lo;
+      for (; c + 8 <= c_hi; c += 8) {
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = h[(size_t)(c + u) * m.ntiles + bin];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part += v[u];
+      }
+      for (; c < c_hi; ++c) part += h[(size_t)c * m.ntiles + bin];
+    }
+    __syncthreads();  // s_part of the previous sweep has been consumed
+    s_part[g * width + lb] = part;
+    __syncthreads();
+    // sweep 2: exclusive prefix over the chunks, starting from the groups before this one
     int run = 0;
-    if (bin < m.ntiles) {
-      int c = 0;
-      for (; c + 8 <= m.nchunks; c += 8) {
+    for (int gg = 0; gg < g; ++gg) run += s_part[gg * width + lb];
+    if (g == 0) {
+      int tot = 0;
+      for (int gg = 0; gg < groups; ++gg) tot += s_part[gg * width + lb];
+      s_tot[bin] = live ? tot : 0;
+    }
+    if (live) {
+      int c = c_lo;
+      for (; c + 8 <= c_hi; c += 8) {
         int v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = h[(size_t)(c + u) * m.ntiles + bin];
@@ -324,13 +379,12 @@ ls_scan_tiles_kernel(Dims m, int *__restrict__ hist, int *__restrict__ tile_ptr)
           run += v[u];
         }
       }
-      for (; c < m.nchunks; ++c) {
+      for (; c < c_hi; ++c) {
         const int v = h[(size_t)c * m.ntiles + bin];
         h[(size_t)c * m.ntiles + bin] = run;
         run += v;
       }
     }
-    s_tot[bin] = run;
   }
   __syncthreads();
   // exclusive scan over the tiles: thread t owns tiles [4t, 4t + 4)
@@ -372,8 +426,12 @@ ls_scan_tiles_kernel(Dims m, int *__restrict__ hist, int *__restrict__ tile_ptr)
 // PLAN 3/4: stable scatter of the runs into per-tile buckets, straight out of the ELL layout.
 // Block = chunk, warp w owns the pixels t = 32w + lane, iteration = run index r.
 // ---------------------------------------------------------------------------------------------
+// The chunk's run keys (voxel ids), staged in shared memory: keys[r][t] for r < kScatRows; runs beyond
+// that (very long rays) are read from the ELL table directly.
+constexpr int kScatRows = 64;
 struct EllInput {
-  const int *run_vox;
+  const int *keys_s;   // shared: [kScatRows][kChunk]
+  const int *run_vox;  // global ELL table
   int frame_chunk, chunk, D;
   int cnt;     // runs of this thread's pixel
   int warp_max;
@@ -381,7 +439,7 @@ struct EllInput {
   __device__ __forceinline__ bool load(int w, int it, int lane, int &key, int &pay) const {
     if (it >= cnt) return false;
     const int t = w * 32 + lane;
-    key = run_vox[ell_slot(frame_chunk, D, it, t)];
+    key = it < kScatRows ? keys_s[it * kChunk + t] : run_vox[ell_slot(frame_chunk, D, it, t)];
     pay = (chunk * D + it) * kChunk + t;
     return true;
   }
@@ -412,16 +470,26 @@ __global__ void __launch_bounds__(kChunk)
 ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_vox,
                         const int *__restrict__ hist, const int *__restrict__ tile_ptr,
                         BucketEnt *__restrict__ bucket) {
-  extern __shared__ int s_cnt[];  // [kChunk / 32][ntiles]
+  extern __shared__ int s_cnt[];  // [kChunk / 32][ntiles], then the staged keys [kScatRows][kChunk]
+  int *keys_s = s_cnt + (kChunk / 32) * m.ntiles;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int frame_chunk = b * m.nchunks + chunk;
   EllInput in;
+  in.keys_s = keys_s;
   in.run_vox = run_vox;
   in.frame_chunk = frame_chunk;
   in.chunk = chunk;
   in.D = m.D;
   in.cnt = run_cnt[(size_t)frame_chunk * kChunk + threadIdx.x];
   in.warp_max = __reduce_max_sync(0xffffffffu, in.cnt);
+  // every key of the chunk in flight at once (one round trip instead of one per batch of runs)
+  {
+    const int nst = min(in.cnt, kScatRows);
+    for (int r = 0; r < nst; ++r)
+      cp_async_4(reinterpret_cast<float *>(keys_s + r * kChunk + threadIdx.x),
+                 reinterpret_cast<const float *>(run_vox + ell_slot(frame_chunk, m.D, r, threadIdx.x)));
+    cp_async_wait_all();  // each thread reads back only what it copied itself
+  }
   sort::stable_scatter_block<kChunk / 32>(
       in, TileOf(), m.ntiles,
       TileBase{tile_ptr + (size_t)b * (m.ntiles + 1), hist + (size_t)frame_chunk * m.ntiles}, s_cnt,
@@ -430,26 +498,21 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
 
 // ---------------------------------------------------------------------------------------------
 // PLAN 4/4: per tile, stable counting sort of the bucket by voxel-in-tile (6 bits): the sorted entries
-// (pixel row | voxel-in-tile, ELL slot of the run) and the CSR offsets of the tile's 64 voxels.  grid (ntiles, B), 128 threads; warp w owns the w-th
+// (pixel row | voxel-in-tile) and the inverse permutation run_dst (ELL slot -> sorted position) that the
+// forward weights pass scatters through.  grid (ntiles, B), 128 threads; warp w owns the w-th
 // quarter of the bucket (contiguous => the canonical order is kept).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinWarps = 4;
 
 __global__ void __launch_bounds__(kFinWarps * 32)
 ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt *__restrict__ bucket,
-                       BucketEnt *__restrict__ vm_ent, int *__restrict__ row_ptr) {
+                       Entry *__restrict__ vm_ent, int *__restrict__ run_dst) {
   __shared__ int s_cnt[kFinWarps][64];
   const int b = blockIdx.y, tile = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1);
   const int lo = tp[tile], hi = tp[tile + 1];
-  int *rp = row_ptr + (size_t)b * (m.V + 1);
-  const int v0 = tile * 64;
-  if (hi == lo) {
-    if (t < 64 && v0 + t < m.V) rp[v0 + t] = lo;
-    if (t == 64 && tile == m.ntiles - 1) rp[m.V] = hi;
-    return;
-  }
+  if (hi == lo) return;
   for (int i = t; i < kFinWarps * 64; i += kFinWarps * 32) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
   const int n = hi - lo;
@@ -480,18 +543,17 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
     int base = lo + x - sum;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (v0 + 2 * lane + k < m.V) rp[v0 + 2 * lane + k] = base;
 #pragma unroll
       for (int w = 0; w < kFinWarps; ++w) {
         s_cnt[w][2 * lane + k] = base;
         base += c[k][w];
       }
     }
-    if (lane == 31 && tile == m.ntiles - 1) rp[m.V] = hi;
   }
   __syncthreads();
   const unsigned lt = lanemask_lt();
-  BucketEnt *ve = vm_ent + (size_t)b * m.cap;
+  Entry *ve = vm_ent + (size_t)b * m.cap;
+  int *rd = run_dst + (size_t)b * m.cap;
   for (int i0 = wb; i0 < we; i0 += 32) {
     const int i = i0 + lane;
     const bool valid = i < we;
@@ -509,7 +571,10 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
       my[dig] = base + __popc(peers);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) ve[base + rank] = e;
+    if (valid) {
+      ve[base + rank].off = e.key;
+      rd[e.slot] = base + rank;
+    }
     __syncwarp();
   }
 }
@@ -519,18 +584,6 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
 // memory with cp.async -- every load of the CTA is in flight at once, rows are read coalesced and
 // exactly once.  col[d * kChunk + t].
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
 __device__ __forceinline__ void stage_columns(float *col, const float *__restrict__ src /*camera base*/,
                                               int D, int P, int p0, bool vec16) {
   const int t = threadIdx.x;
@@ -585,9 +638,12 @@ __device__ __forceinline__ float softmax_column(float *col, int D, int t) {
 // pixel-major (ELL slot of the run; coalesced).  The forward reduce gathers them through the slot
 // index its sorted entries carry.
 // ---------------------------------------------------------------------------------------------
+// vm_ent_out != nullptr: forward, the weight goes to the run's voxel-major entry (through run_dst);
+// else backward, pixel-major w_pm_out.
 __device__ __forceinline__ void weights_role(const Dims &m, const float *__restrict__ height, int vec16,
                                              const int *__restrict__ run_cnt, const int *__restrict__ run_d,
-                                             float *__restrict__ w_pm_out, float *col, int b, int chunk) {
+                                             const int *__restrict__ run_dst, float *__restrict__ w_pm_out,
+                                             Entry *__restrict__ vm_ent_out, float *col, int b, int chunk) {
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;
   const int t = threadIdx.x;
@@ -596,14 +652,41 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   if (p0 + t >= m.P) return;
   const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
   if (cnt == 0) return;
+  // the first run descriptors are requested before the softmax so that their latency hides behind it
+  constexpr int kPre = 8;
+  int pre_d[kPre], pre_dst[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    pre_d[u] = 0; pre_dst[u] = 0;
+    if (u < cnt) {
+      const size_t sl = ell_slot(frame_chunk, m.D, u, t);
+      pre_d[u] = run_d[sl];
+      if (vm_ent_out) pre_dst[u] = run_dst[sl];
+    }
+  }
   const float scale = m.logits ? softmax_column(col, m.D, t) : 1.0f;
-  // batch the (strided) run descriptors 4 at a time
-  for (int r0 = 0; r0 < cnt; r0 += 4) {
-    int packed[4];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    if (u < cnt) {
+      const int d0 = pre_d[u] & 0xffff, d1 = pre_d[u] >> 16;
+      float acc = 0.0f;
+      for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
+      const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
+      if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + pre_dst[u]].w = wgt;
+      else w_pm_out[ell_slot(frame_chunk, m.D, u, t)] = wgt;
+    }
+  }
+  // the rest in batches of 4 (strided descriptors)
+  for (int r0 = kPre; r0 < cnt; r0 += 4) {
+    int packed[4], dst[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      packed[u] = 0;
-      if (r0 + u < cnt) packed[u] = run_d[ell_slot(frame_chunk, m.D, r0 + u, t)];
+      packed[u] = 0; dst[u] = 0;
+      if (r0 + u < cnt) {
+        const size_t sl = ell_slot(frame_chunk, m.D, r0 + u, t);
+        packed[u] = run_d[sl];
+        if (vm_ent_out) dst[u] = run_dst[sl];
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -611,7 +694,9 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
         const int d0 = packed[u] & 0xffff, d1 = packed[u] >> 16;
         float acc = 0.0f;
         for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-        w_pm_out[ell_slot(frame_chunk, m.D, r0 + u, t)] = m.logits ? __fmul_rn(acc, scale) : acc;
+        const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
+        if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + dst[u]].w = wgt;
+        else w_pm_out[ell_slot(frame_chunk, m.D, r0 + u, t)] = wgt;
       }
     }
   }
@@ -660,10 +745,12 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
 template <typename CT>
 __global__ void __launch_bounds__(kChunk)
 ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
-                    const int *__restrict__ run_d, float *__restrict__ w_pm_out,
+                    const int *__restrict__ run_d, const int *__restrict__ run_dst,
+                    float *__restrict__ w_pm_out, Entry *__restrict__ vm_ent_out,
                     const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm) {
   extern __shared__ float lift_smem[];
-  if (blockIdx.z == 0) weights_role(m, height, vec16, run_cnt, run_d, w_pm_out, lift_smem, blockIdx.y, blockIdx.x);
+  if (blockIdx.z == 0)
+    weights_role(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x);
   else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x);
 }
 
@@ -778,24 +865,25 @@ struct StreamAcc {
   }
 };
 
+// entry j of the tile's sorted list: from the staged copy in shared memory, or (huge tiles) from the plan
+template <bool STAGED>
+__device__ __forceinline__ Entry load_entry(const Entry *__restrict__ ent, int j) {
+  if (STAGED) return ent[j];
+  const uint2 t = __ldg(reinterpret_cast<const uint2 *>(ent + j));
+  Entry e;
+  e.off = t.x;
+  e.w = __uint_as_float(t.y);
+  return e;
+}
+
 // One stream = one G-lane group walking the slice [j0, j1) of the tile's sorted entries, two entries in
-// flight.  STAGED: entries (row | voxel, weight) come from shared memory; otherwise (huge tiles) from the
-// plan in global memory, the weight gathered through the entry's slot index.
+// flight.
 template <typename CT, int G, int NV, bool STAGED>
 __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, bool &head,
-                                            const Entry *__restrict__ ent, const float *__restrict__ wf,
-                                            int j0, int j1, const int *s_rp,
+                                            const Entry *__restrict__ ent, int tile_lo, int j0, int j1,
                                             const unsigned char *__restrict__ lane_rows, unsigned tile_lane,
                                             float *my_head, int l, unsigned box_bytes) {
   constexpr unsigned kRowBytes = 4 * G * NV * sizeof(CT);
-  auto load_entry = [&](int j, Entry &en) {
-    if (STAGED) en = ent[j];
-    else {
-      const uint2 t = __ldg(reinterpret_cast<const uint2 *>(ent + j));
-      en.off = t.x;
-      en.w = __ldg(wf + t.y);
-    }
-  };
   auto load_row = [&](const Entry &en, float (&r)[NV][4]) {
     const unsigned char *row = lane_rows + (size_t)(en.off >> 6) * kRowBytes;
 #pragma unroll
@@ -818,27 +906,22 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
     }
   };
   if (j0 >= j1) return;
-  {
-    Entry e0;
-    load_entry(j0, e0);
-    head = j0 > s_rp[e0.off & 63u];
-  }
+  // the slice continues a voxel of the previous slice iff the entry before it carries the same voxel
+  if (j0 > tile_lo)
+    head = ((load_entry<STAGED>(ent, j0 - 1).off ^ load_entry<STAGED>(ent, j0).off) & 63u) == 0;
   int j = j0;
 #pragma unroll 1
   for (; j + 2 <= j1; j += 2) {
-    Entry ea, eb;
     float ra[NV][4], rb[NV][4];
-    load_entry(j, ea);
-    load_entry(j + 1, eb);
+    const Entry ea = load_entry<STAGED>(ent, j), eb = load_entry<STAGED>(ent, j + 1);
     load_row(ea, ra);
     load_row(eb, rb);
     accumulate(ea, ra);
     accumulate(eb, rb);
   }
   if (j < j1) {
-    Entry ea;
     float ra[NV][4];
-    load_entry(j, ea);
+    const Entry ea = load_entry<STAGED>(ent, j);
     load_row(ea, ra);
     accumulate(ea, ra);
   }
@@ -860,9 +943,8 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
 // ---------------------------------------------------------------------------------------------
 template <typename CT, int G, int NV, int NSTR>
 __global__ void __launch_bounds__(NSTR * G)
-ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ row_ptr,
-                 const Entry *__restrict__ vm_ent, const float *__restrict__ w_pm,
-                 float *__restrict__ bev, int vec_out) {
+ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ tile_ptr,
+                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int kThreads = NSTR * G;
   constexpr int kRows = 4 * G * NV;                  // = Cpad rows (rows >= C are scratch)
@@ -870,17 +952,14 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   unsigned char *tile = smem_raw;                                          // 2 boxes x kRows x 128 B
   float *s_head = reinterpret_cast<float *>(smem_raw + 2 * kBoxBytes);     // NSTR x kRows partial sums
   Entry *s_ent = reinterpret_cast<Entry *>(s_head + NSTR * kRows);         // kStageE entries
-  __shared__ int s_rp[kTileV + 1];
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int l = tid & (G - 1);
   const int s = tid / G;  // stream index: consecutive streams sit in one warp
   const int v0 = blockIdx.x * kTileV;
   const int nv = min(kTileV, m.V - v0);
-  const int *rp = row_ptr + (size_t)b * (m.V + 1) + v0;
-  if (tid <= kTileV) s_rp[tid] = rp[min(tid, nv)];
-  __syncthreads();
-  const int tile_lo = s_rp[0], tile_hi = s_rp[kTileV];
+  const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1) + blockIdx.x;
+  const int tile_lo = __ldg(tp), tile_hi = __ldg(tp + 1);
   float *out = bev + (size_t)b * m.C * m.V + v0;
 
   // thread <-> (channel row c0 + kThreads/16 * i, 16-byte chunk q) of the tile for the copy-out loops
@@ -906,18 +985,11 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   const int n_t = tile_hi - tile_lo;
   const bool staged = n_t <= kStageE;
   const Entry *ent = vm_ent + (size_t)b * m.cap;
-  const float *wf = w_pm + (size_t)b * m.cap;
-  if (staged) {
-    for (int i = tid; i < n_t; i += kThreads) {
-      const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ent + tile_lo + i));
-      Entry o;
-      o.off = e.x;
-      o.w = __ldg(wf + e.y);
-      s_ent[i] = o;
-    }
-  }
+  if (staged)
+    for (int i = tid; i < n_t; i += kThreads) cp_async_8(s_ent + i, ent + tile_lo + i);
   for (int i = tid; i < 2 * (int)kBoxBytes / 16; i += kThreads)
     reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  cp_async_wait_all();
   __syncthreads();
 
   // stream s owns the entries [j0, j1) of the tile: equal slices
@@ -932,23 +1004,30 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ro
   acc.clear();
   int cur = -1;         // voxel (in tile) being accumulated
   bool head = false;    // the segment being accumulated continues a voxel started by an earlier stream
+  const Entry *se = s_ent - tile_lo;  // staged entries, addressed like the plan's
   if (staged)
-    stream_loop<CT, G, NV, true>(acc, cur, head, s_ent - tile_lo, nullptr, j0, j1, s_rp, lane_rows, tile_lane,
-                                 my_head, l, kBoxBytes);
+    stream_loop<CT, G, NV, true>(acc, cur, head, se, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes);
   else
-    stream_loop<CT, G, NV, false>(acc, cur, head, ent, wf, j0, j1, s_rp, lane_rows, tile_lane, my_head, l,
-                                  kBoxBytes);
+    stream_loop<CT, G, NV, false>(acc, cur, head, ent, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes);
+  // voxel (in tile) of entry j
+  auto vox_at = [&](int j) -> int {
+    return (int)((staged ? load_entry<true>(se, j) : load_entry<false>(ent, j)).off & 63u);
+  };
   // the last segment of the slice: complete iff the slice ends on the voxel's last entry
   bool tail = false;
   if (cur >= 0) {
     if (head) acc.store_head(my_head, l);                 // the whole slice lies inside one earlier voxel
-    else if (s_rp[cur + 1] == j1) acc.flush_tile(tile_lane, l, kBoxBytes, cur);
+    else if (j1 == tile_hi || vox_at(j1) != cur) acc.flush_tile(tile_lane, l, kBoxBytes, cur);
     else tail = true;                                      // later slices continue this voxel
   }
   __syncthreads();
   if (tail) {
-    const int vend = s_rp[cur + 1];
-    for (int k = s + 1; k < NSTR && tile_lo + k * E < vend; ++k) acc.add_head(s_head + k * kRows, l);
+    // slices s+1, s+2, ... that start inside this voxel parked their partial sums: add them in order
+    for (int k = s + 1; k < NSTR; ++k) {
+      const int jk = tile_lo + k * E;
+      if (jk >= tile_hi || vox_at(jk) != cur) break;
+      acc.add_head(s_head + k * kRows, l);
+    }
     acc.flush_tile(tile_lane, l, kBoxBytes, cur);
   }
   __syncthreads();
@@ -1176,7 +1255,7 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
   ls_reduce_kernel<CT, G, NV, NSTR><<<grid, NSTR * G, smem, s>>>(
-      m, static_cast<const CT *>(w.ctxT), w.row_ptr, w.vm_ent, w.w_pm, bev, vec_out);
+      m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out);
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
 }
@@ -1219,7 +1298,8 @@ int launch_backward_gather(const Dims &m, const Workspace &w, int gpad, cudaStre
 
 // weights + context rows in one launch (forward and backward need both)
 int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const float *height, const void *context,
-                     cudaStream_t s) {
+                     bool forward, cudaStream_t s) {
+  Entry *vm_out = forward ? w.vm_ent : nullptr;
   dim3 grid(m.nchunks, m.B, 2);
   const size_t smem = sizeof(float) * (size_t)(m.D > m.C ? m.D * kChunk : m.C * (kChunk + 1));
   const size_t smem2 = sizeof(float) * (size_t)kChunk * m.D > smem ? sizeof(float) * (size_t)kChunk * m.D : smem;
@@ -1227,12 +1307,12 @@ int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const flo
   if (ctx_dtype == SGV3D_DTYPE_BF16) {
     if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16>, smem2)) return rc;
     ls_lift_prep_kernel<__nv_bfloat16><<<grid, kChunk, smem2, s>>>(
-        m, height, vec16, w.run_cnt, w.run_d, w.w_pm, static_cast<const __nv_bfloat16 *>(context),
+        m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm, vm_out, static_cast<const __nv_bfloat16 *>(context),
         static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m));
   } else {
     if (int rc = set_smem(ls_lift_prep_kernel<float>, smem2)) return rc;
-    ls_lift_prep_kernel<float><<<grid, kChunk, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.w_pm,
-                                                          static_cast<const float *>(context),
+    ls_lift_prep_kernel<float><<<grid, kChunk, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
+                                                          vm_out, static_cast<const float *>(context),
                                                           static_cast<float *>(w.ctxT), row_perm(m));
   }
   SGV3D_CHECK_LAUNCH("ls_lift_prep_kernel");
@@ -1292,12 +1372,12 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   SGV3D_CHECK_LAUNCH("ls_plan_runs_kernel");
   ls_scan_tiles_kernel<<<m.B, kScanThreads, 0, s>>>(m, w.hist, w.tile_ptr);
   SGV3D_CHECK_LAUNCH("ls_scan_tiles_kernel");
-  const size_t csm = sizeof(int) * (kChunk / 32) * m.ntiles;
+  const size_t csm = sizeof(int) * ((kChunk / 32) * m.ntiles + kScatRows * kChunk);
   if (int rc = set_smem(ls_scatter_tiles_kernel, csm)) return rc;
   ls_scatter_tiles_kernel<<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
   SGV3D_CHECK_LAUNCH("ls_scatter_tiles_kernel");
   ls_finish_tiles_kernel<<<dim3(m.ntiles, m.B), kFinWarps * 32, 0, s>>>(
-      m, w.tile_ptr, w.bucket, reinterpret_cast<BucketEnt *>(w.vm_ent), w.row_ptr);
+      m, w.tile_ptr, w.bucket, w.vm_ent, w.run_dst);
   SGV3D_CHECK_LAUNCH("ls_finish_tiles_kernel");
   return SGV3D_OK;
 }
@@ -1313,7 +1393,7 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
-  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, s)) return rc;
+  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, true, s)) return rc;
   if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
   return launch_reduce<float>(m, w, bev, s);
 }
@@ -1332,7 +1412,7 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   const int gpad = m.Cpad;  // gradient rows share the context rows' (permuted) channel layout
-  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, s)) return rc;
+  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, false, s)) return rc;
   launch_transpose_pad<float, float, 1>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
                                         (size_t)m.V * gpad, s, row_perm(m));
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_bev)");
