@@ -249,7 +249,7 @@ struct FastRay {
 
   // voxel id (y*X + x, -1 dropped) of the point at bin height z; `bad` is raised for a point whose
   // identity-BDA shortcut is not provably exact.  a2 = row 2 of A, me = rows 0..2 of Me (registers).
-  __device__ __forceinline__ int voxel(const float (&a2)[4], const float (&me)[12], float ref_h,
+  __device__ __forceinline__ int voxel(const float *a2, const float *me, float ref_h,
                                        bool check_finite, const Grid &g, float z, bool &bad) const {
     const float p0z = dot2_tail<ARITH>(head2, a2, z, 1.0f);
     const float hgt = __fadd_rn(__fmul_rn(-1.0f, p0z), ref_h);
@@ -266,6 +266,74 @@ struct FastRay {
     const int iy = PixelRay<ARITH>::quantize_guarded(gy, g.lower[1], g.size[1], g.rcp_size[1]);
     if ((unsigned)iy >= (unsigned)g.Y) return -1;
     return iy * g.X + ix;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Guarded linear shortcut on top of FastRay.  For a qualified pixel the real-valued ego coordinates are
+// LINEAR in the bin's height  hgt = RN(ref_h - p0z):   G_r(hgt) = kappa_r * hgt + Me_r3,
+// kappa_r = (sum_i Me_ri * pv_i) / pv1,  so the real-valued voxel coordinate is  Q(hgt) = K * hgt + C.
+// The reference's fp32 chain (ratio, e_i, dot4, subtract, divide: FastRay::voxel) deviates from Q by at
+// most  8.3 u (S + |lower|) / size   with u = 2^-24 and  S = sum_i |Me_ri pv_i| rho_max + |Me_r3|
+// (standard forward error analysis: 1 rounding in ratio, 1 in each e_i, <= 4 in the dot product, 1 in the
+// subtraction, 1 in the division; rho_max bounds |hgt / pv1| over all bins), and  q' = fma(hgt, K, C)
+// with K, C rounded from fp64 deviates from Q by at most 3 u (S + |lower|) / size.  With the guard
+// band  delta = 32 u (S + |lower|) / size  (>= 2.8x the sum of both): whenever q' is farther than delta
+// from every integer, trunc(q') == trunc(q_reference) -- truncation only jumps at integers -- and the
+// index is taken from q'.  Otherwise (about 0.1 % of the points), and for NaN / overflow (the comparison
+// fails), the exact chain decides.  The z-range test is resolved once per pixel when the whole height
+// range maps strictly inside the grid's z extent by more than the same kind of margin; if not, the
+// pixel uses the exact chain throughout.  The voxel index can therefore never differ from the exact
+// kernel's: it is either proven equal or computed by it.
+// ---------------------------------------------------------------------------------------------
+struct LinearGuard {
+  float kx, cx, dx;  // q'_x = fma(hgt, kx, cx), guard band dx (voxel units)
+  float ky, cy, dy;
+  bool ok;           // false: use the exact chain for every bin of this pixel
+
+  // pv*: the pixel's virtual-camera ray (FastRay); me: rows 0..2 of Me; p0z_lo / p0z_hi: bounds of p0z over
+  // the bins; ref_h: camera height.
+  __device__ __forceinline__ void init(float pv0, float pv1, float pv2, const float *me, float ref_h,
+                                       float p0z_lo, float p0z_hi, const Grid &g) {
+    const double u32 = 1.9073486328125e-06;  // 32 * 2^-24
+    const double rp = 1.0 / (double)pv1;
+    const double h_lo = (double)ref_h - (double)p0z_hi, h_hi = (double)ref_h - (double)p0z_lo;
+    const double h_abs = fmax(fabs(h_lo), fabs(h_hi)) * 1.000001 + 1e-30;
+    const double rho = h_abs * fabs(rp);
+    double kap[3], S[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double t0 = (double)me[4 * r + 0] * pv0, t1 = (double)me[4 * r + 1] * pv1, t2 = (double)me[4 * r + 2] * pv2;
+      kap[r] = (t0 + t1 + t2) * rp;
+      S[r] = (fabs(t0) + fabs(t1) + fabs(t2)) * rho + fabs((double)me[4 * r + 3]);
+    }
+    const double isx = 1.0 / (double)g.size[0], isy = 1.0 / (double)g.size[1];
+    kx = (float)(kap[0] * isx); cx = (float)(((double)me[3] - (double)g.lower[0]) * isx);
+    ky = (float)(kap[1] * isy); cy = (float)(((double)me[7] - (double)g.lower[1]) * isy);
+    const double ddx = u32 * (S[0] + fabs((double)g.lower[0])) * isx + 1e-30;
+    const double ddy = u32 * (S[1] + fabs((double)g.lower[1])) * isy + 1e-30;
+    dx = (float)(ddx * 1.0000002);
+    dy = (float)(ddy * 1.0000002);
+    // z: t_z(hgt) = kap2 * hgt + (Me_23 - lower_z) must stay inside (zt_lo, zt_hi) by the margin over the whole
+    // height range (linear => the two ends decide)
+    const double cz = (double)me[11] - (double)g.lower[2];
+    const double dz = u32 * (S[2] + fabs((double)g.lower[2])) + 1e-30;
+    const double tz_a = kap[2] * h_lo + cz, tz_b = kap[2] * h_hi + cz;
+    const bool z_in = fmin(tz_a, tz_b) - dz > (double)g.zt_lo && fmax(tz_a, tz_b) + dz < (double)g.zt_hi;
+    // every intermediate of the exact chain must be comfortably finite (then e_i, g_r are finite and the
+    // identity-bda shortcut of FastRay holds as well)
+    const double big = fmax(fmax(fabs((double)pv0), fabs((double)pv1)), fabs((double)pv2)) * rho;
+    ok = z_in && ddx < 0.25 && ddy < 0.25 && big < 1e30 && S[0] < 1e30 && S[1] < 1e30 && S[2] < 1e30 &&
+         fabs((double)pv1) > 1e-30;  // NaN anywhere makes a comparison fail => not ok
+  }
+
+  // voxel id (y*X + x, -1 dropped) from the linear form; `safe` = proven equal to the exact chain
+  __device__ __forceinline__ int voxel(float hgt, const Grid &g, bool &safe) const {
+    const float qx = __fmaf_rn(hgt, kx, cx), qy = __fmaf_rn(hgt, ky, cy);
+    const float ex = fabsf(__fsub_rn(qx, rintf(qx))), ey = fabsf(__fsub_rn(qy, rintf(qy)));
+    safe = ex > dx && ey > dy;  // false for NaN
+    const int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
+    return ((unsigned)ix < (unsigned)g.X && (unsigned)iy < (unsigned)g.Y) ? iy * g.X + ix : -1;
   }
 };
 

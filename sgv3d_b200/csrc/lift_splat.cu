@@ -239,7 +239,7 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
                          int *__restrict__ run_cnt, int *__restrict__ run_vox, int *__restrict__ run_d,
                          int *__restrict__ hist, int *__restrict__ chunk_done) {
   __shared__ geom::Camera cam;
-  __shared__ int s_fast;
+  __shared__ int s_fast, s_zmin, s_zmax;  // z range of the bins as order-preserving ints
   extern __shared__ float z_s[];
   int *s_hist = reinterpret_cast<int *>(z_s + m.D);
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -248,11 +248,17 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
   const int t = threadIdx.x;
   const int frame_chunk = b * m.nchunks + chunk;
   geom::load_camera(&cam, ida_inv, mv, me, bda, ref_h, bn, b);
+  if (t == 0) { s_zmin = 0x7fffffff; s_zmax = (int)0x80000000; }
+  __syncthreads();
   bool z_ok = true;
   for (int d = t; d < m.D; d += kChunk) {
     const float z = z_tab[d];
     z_s[d] = z;
     z_ok = z_ok && (fabsf(z) < INFINITY);
+    int zi = __float_as_int(z);
+    zi ^= (zi >> 31) & 0x7fffffff;  // monotone float -> int map
+    atomicMin(&s_zmin, zi);
+    atomicMax(&s_zmax, zi);
   }
   for (int i = t; i < m.ntiles; i += kChunk) s_hist[i] = 0;
   if (!__syncthreads_and(z_ok)) {  // (also publishes cam / z_s / s_hist)
@@ -272,13 +278,32 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
     const int h = p / m.fW, w = p - h * m.fW;
     geom::FastRay<ARITH> ray;
     bad = !ray.init(cam, u_tab[w], v_tab[h], z_s[0]);
-    float a2[4], mer[12];
+    float a2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) a2[i] = cam.A[8 + i];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) mer[i] = cam.Me[i];
+    const float *mer = cam.Me;  // shared memory: only the (rare) exact chain reads it
     const float rh = cam.ref_h;
     const bool check_finite = cam.has_bda != 0;
+    // linear shortcut: p0z is monotone in z for every evaluation order, so its range over the bins is
+    // spanned by the two extreme bin values
+    geom::LinearGuard lg;
+    {
+      int za = s_zmin, zb = s_zmax;
+      za ^= (za >> 31) & 0x7fffffff;
+      zb ^= (zb >> 31) & 0x7fffffff;
+      const float pa = geom::dot2_tail<ARITH>(ray.head2, a2, __int_as_float(za), 1.0f);
+      const float pb = geom::dot2_tail<ARITH>(ray.head2, a2, __int_as_float(zb), 1.0f);
+      lg.init(ray.pv0, ray.pv1, ray.pv2, mer, rh, fminf(pa, pb), fmaxf(pa, pb), grid);
+      if (bad) lg.ok = false;
+    }
+    auto voxel_of_bin = [&](float z) -> int {
+      const float p0z = geom::dot2_tail<ARITH>(ray.head2, a2, z, 1.0f);
+      const float hgt = __fadd_rn(__fmul_rn(-1.0f, p0z), rh);
+      bool safe;
+      int v = lg.voxel(hgt, grid, safe);
+      if (!(lg.ok && safe)) v = ray.voxel(a2, mer, rh, check_finite, grid, z, bad);
+      return v;
+    };
     int cur = -1, d0 = 0;
     auto step = [&](int d, int vox) {
       if (vox != cur) {
@@ -295,13 +320,13 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
     };
     int d = 0;
     for (; d + 2 <= m.D; d += 2) {
-      const int v0 = ray.voxel(a2, mer, rh, check_finite, grid, z_s[d], bad);
-      const int v1 = ray.voxel(a2, mer, rh, check_finite, grid, z_s[d + 1], bad);
+      const int v0 = voxel_of_bin(z_s[d]);
+      const int v1 = voxel_of_bin(z_s[d + 1]);
       step(d, v0);
       step(d + 1, v1);
     }
     if (d < m.D) {
-      step(d, ray.voxel(a2, mer, rh, check_finite, grid, z_s[d], bad));
+      step(d, voxel_of_bin(z_s[d]));
       ++d;
     }
     step(m.D, -2);  // sentinel closes the last run

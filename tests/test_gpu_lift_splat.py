@@ -202,3 +202,31 @@ def test_fused_softmax_on_strided_head_output():
     want = CO.lift_splat_forward64(idx, big[:, :D].double().softmax(1).float().cpu().numpy(),
                                    big[:, D:D + C].cpu().numpy(), *shape.grid)
     np.testing.assert_allclose(bev_a.detach().cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("shape_name,batch,arith", [("dair_r50", 48, 2), ("rope3d_r50", 32, 2), ("dair_r50_256", 16, 2),
+                                                    ("rope3d_r101_140", 8, 0), ("sgv3d_bsm_r50", 8, 1),
+                                                    ("rope3d_native", 16, 2)])
+def test_plan_shortcuts_match_the_exact_geometry_kernel(shape_name, batch, arith):
+    """Full-size, many calibrations: the plan's fast index paths (z-preserving IDA, identity BDA, guarded
+    linear shortcut) against the standalone geometry kernel, which always evaluates the full chain.
+    Bit-exact voxel id / kept mask for every point (tens of millions per case)."""
+    from sgv3d_b200.view_transform import LiftSplatPlan, geometry_indices
+    shape = get_shape(shape_name)
+    fr = oracle_frustum(shape)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    X, Y, Z = shape.grid
+    total = 0
+    for seed, bda in ((101, "identity"), (202, None)):
+        mats = make_mats(shape, batch, 1, seed=seed, bda=bda)
+        dev = {k: (v.cuda() if v is not None else None) for k, v in mats.items()}
+        args = (dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"], dev["reference_heights"], dev["bda"])
+        plan = LiftSplatPlan(fr, *args, vc, vs, shape.grid, shape.channels, arith=arith)
+        idx = geometry_indices(fr, *args, vc, vs, arith=arith)
+        kept = ((idx[..., 0] >= 0) & (idx[..., 0] < X) & (idx[..., 1] >= 0) & (idx[..., 1] < Y)
+                & (idx[..., 2] >= 0) & (idx[..., 2] < Z))
+        want = torch.where(kept, idx[..., 1] * X + idx[..., 0], torch.full_like(idx[..., 0], -1))
+        got = plan.expand()
+        assert int((got != want).sum()) == 0
+        total += got.numel()
+    assert total >= 2 * batch * shape.points_per_frame
