@@ -305,12 +305,16 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
       return v;
     };
     int cur = -1, d0 = 0;
+    // this chunk's block of the ELL table; run r of this pixel sits at element r * kChunk + t
+    int *const rv = run_vox + ell_slot(frame_chunk, m.D, 0, 0);
+    int *const rd = run_d + ell_slot(frame_chunk, m.D, 0, 0);
+    int eo = t;
     auto step = [&](int d, int vox) {
       if (vox != cur) {
         if (cur >= 0) {
-          const size_t s = ell_slot(frame_chunk, m.D, r, t);
-          run_vox[s] = cur;
-          run_d[s] = d0 | (d << 16);
+          rv[eo] = cur;
+          rd[eo] = d0 | (d << 16);
+          eo += kChunk;
           atomicAdd(&s_hist[cur >> 6], 1);
           ++r;
         }
@@ -322,8 +326,10 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
     for (; d + 2 <= m.D; d += 2) {
       const int v0 = voxel_of_bin(z_s[d]);
       const int v1 = voxel_of_bin(z_s[d + 1]);
-      step(d, v0);
-      step(d + 1, v1);
+      if (v0 != cur || v1 != cur) {  // one divergent region per pair of bins
+        step(d, v0);
+        step(d + 1, v1);
+      }
     }
     if (d < m.D) {
       step(d, voxel_of_bin(z_s[d]));

@@ -230,3 +230,17 @@ def test_plan_shortcuts_match_the_exact_geometry_kernel(shape_name, batch, arith
         assert int((got != want).sum()) == 0
         total += got.numel()
     assert total >= 2 * batch * shape.points_per_frame
+
+
+@pytest.mark.parametrize("batch", [1, 2, 7, 32])
+def test_stacked_inverse_is_bit_identical(batch):
+    """camera_matrices() inverts ida / intrin / sensor2virtual with ONE batched call; every 4x4 must keep the
+    bits the reference's three separate ``inverse`` calls produce (lss_fpn.py:361,367,392)."""
+    from sgv3d_b200.view_transform import camera_matrices
+    for seed, bda in ((3, "identity"), (4, "random")):
+        m = make_mats(get_shape("rope3d_r50"), batch, 2, seed=seed, bda=bda)
+        s2e, s2v, k, ida = (m[n].cuda() for n in ("sensor2ego", "sensor2virtual", "intrin", "ida"))
+        got = camera_matrices(s2e, s2v, k, ida)
+        want = (ida.inverse(), s2v.matmul(torch.inverse(k)), s2e.matmul(torch.inverse(s2v)))
+        for g, w in zip(got, want):
+            assert torch.equal(g.contiguous().view(torch.int32), w.contiguous().view(torch.int32))
