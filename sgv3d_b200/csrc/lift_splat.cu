@@ -530,8 +530,7 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
 // ---------------------------------------------------------------------------------------------
 // PLAN 4/4: per tile, stable counting sort of the bucket by voxel-in-tile (6 bits): the sorted entries
 // (pixel row | voxel-in-tile) and the inverse permutation run_dst (ELL slot -> sorted position) that the
-// forward weights pass scatters through.  grid (ntiles, B), 128 threads; warp w owns the w-th
-// quarter of the bucket (contiguous => the canonical order is kept).
+// forward weights pass scatters through.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinWarps = 4;
 
@@ -746,27 +745,34 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int p0 = ci * kChunk;
   const int npx = min(kChunk, m.P - p0);
-  const CT *src = context + (size_t)(b * m.Nc + n) * m.cs + p0;
-  if (sizeof(CT) == 4) {
-    if (t < npx)
-      for (int c = 0; c < m.C; ++c)
-        cp_async_4(smem + c * kLd + t, reinterpret_cast<const float *>(src) + (size_t)c * m.P + t);
-    cp_async_wait_all();
-  } else {
-    if (t < npx)
-      for (int c = 0; c < m.C; ++c) smem[c * kLd + t] = to_f32<CT>(src[(size_t)c * m.P + t]);
+  const CT *src = context + (size_t)(b * m.Nc + n) * m.cs + p0 + t;
+  if (t < npx) {
+    float *sp = smem + t;
+    if (sizeof(CT) == 4) {
+#pragma unroll 4
+      for (int c = 0; c < m.C; ++c, sp += kLd, src += m.P) cp_async_4(sp, reinterpret_cast<const float *>(src));
+    } else {
+#pragma unroll 4
+      for (int c = 0; c < m.C; ++c, sp += kLd, src += m.P) *sp = to_f32<CT>(*src);
+    }
   }
+  cp_async_wait_all();
   __syncthreads();
   CT *dst = ctxT + ((size_t)(b * m.Nc + n) * m.P + p0) * m.Cpad;
-  // lane <-> element of the row (3 pieces of 32 elements cover Cpad <= 96; loop for wider rows)
+  // lane <-> element of the row (3 pieces of 32 elements cover Cpad <= 96; loop for wider rows); everything
+  // that depends on the element only is hoisted out of the pixel loop
   for (int e0 = 0; e0 < m.Cpad; e0 += 32) {
     const int e = e0 + lane;
-    const int c = e < m.Cpad ? perm.chan(e) : m.C;
-    const bool live = e < m.Cpad;
-    const bool real = c < m.C;
-    for (int px = wid; px < npx; px += kChunk / 32) {
-      const float v = real ? smem[c * kLd + px] : 0.0f;
-      if (live) dst[(size_t)px * m.Cpad + e] = from_f32<CT>(v);
+    if (e >= m.Cpad) continue;
+    const int c = perm.chan(e);
+    CT *dp = dst + (size_t)wid * m.Cpad + e;
+    const size_t dstep = (size_t)(kChunk / 32) * m.Cpad;
+    if (c < m.C) {
+      const float *sp = smem + c * kLd + wid;
+#pragma unroll 4
+      for (int px = wid; px < npx; px += kChunk / 32, sp += kChunk / 32, dp += dstep) *dp = from_f32<CT>(*sp);
+    } else {
+      for (int px = wid; px < npx; px += kChunk / 32, dp += dstep) *dp = from_f32<CT>(0.0f);
     }
   }
 }
