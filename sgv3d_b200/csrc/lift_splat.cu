@@ -1183,6 +1183,245 @@ ls_backward_gather_kernel(Dims m, int gpad, const CT *__restrict__ ctxT, const f
 }
 
 // ---------------------------------------------------------------------------------------------
+// BACKWARD: grad_bev (B, C, Y, X) -> one channels-last row per voxel (permuted layout), only for the
+// 64-voxel tiles that received at least one run (the rows of untouched voxels are never read).
+// grid (ntiles, B), 256 threads; reads 256-byte pieces of the channel planes, writes whole rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ls_grad_rows_kernel(Dims m, const float *__restrict__ grad_bev, const int *__restrict__ tile_ptr,
+                    float *__restrict__ gT, RowPerm perm) {
+  extern __shared__ float gsm[];  // [C][65]
+  constexpr int kLd = kTileV + 1;
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1) + tile;
+  if (__ldg(tp) == __ldg(tp + 1)) return;
+  const int v0 = tile * kTileV;
+  const int nv = min(kTileV, m.V - v0);
+  const int t = threadIdx.x & 63, q = threadIdx.x >> 6;
+  if (t < nv) {
+    const float *src = grad_bev + (size_t)b * m.C * m.V + v0 + t;
+    for (int c = q; c < m.C; c += 4) cp_async_4(gsm + c * kLd + t, src + (size_t)c * m.V);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float *dst = gT + ((size_t)b * m.V + v0) * m.Cpad;
+  for (int e0 = 0; e0 < m.Cpad; e0 += 32) {
+    const int e = e0 + lane;
+    if (e >= m.Cpad) continue;
+    const int c = perm.chan(e);
+    float *dp = dst + (size_t)wid * m.Cpad + e;
+    const size_t dstep = (size_t)8 * m.Cpad;
+    if (c < m.C) {
+      const float *sp = gsm + c * kLd + wid;
+#pragma unroll 4
+      for (int v = wid; v < nv; v += 8, sp += 8, dp += dstep) *dp = *sp;
+    } else {
+      for (int v = wid; v < nv; v += 8, dp += dstep) *dp = 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BACKWARD, fused per pixel chunk (rows of <= 96 channels): one CTA = 64 pixels x 4 lanes.
+//   1. the chunk's D x 64 height block and C x 64 context block are staged with cp.async (coalesced,
+//      all loads in flight at once);
+//   2. a 4-lane group owns one pixel: softmax over D (lane l takes bins d = l mod 4: the same four
+//      summation chains, combined in the same order, as the forward weights pass), run weights
+//      w_r = sum_{d in run} p_d (lane r mod 4, ascending d);
+//   3. per run: 128-bit gather of the voxel's gradient row G (channels-last, permuted layout: lane l holds
+//      channels l + 4j), g_ctx += w_r * G (packed FFMA2), gw_r = <ctx, G> (butterfly over the 4 lanes,
+//      fixed order); S = sum_r w_r gw_r for the softmax backward;
+//   4. g_height[d] = gw[run(d)] (0 for dropped bins), or p_d (gw - S) when the softmax is fused;
+//      g_ctx leaves through the shared-memory tile as coalesced NCHW rows.
+// No atomics, fixed summation orders => bitwise reproducible.  Replaces weights + gather + expand +
+// the g_ctx transpose of the unfused path (four passes over the run table) with one.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwdPix = 64;    // pixels per CTA (half a plan chunk)
+constexpr int kBwdLd = kBwdPix + 1;
+
+template <typename CT, int NV>
+__global__ void __launch_bounds__(kBwdPix * 4, 2)
+ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__restrict__ context,
+                         const float *__restrict__ gT, const int *__restrict__ run_cnt,
+                         const int *__restrict__ run_vox, const int *__restrict__ run_d,
+                         float *__restrict__ w_pm, float *__restrict__ gw_pm, float *__restrict__ g_height,
+                         float *__restrict__ g_context) {
+  constexpr int G = 4, NJ = 4 * NV;   // NJ channels per lane
+  constexpr int kRowF = 4 * G * NV;   // floats per gradient row (= Cpad)
+  extern __shared__ float bsm[];
+  float *col = bsm;                          // [D][64]   height bins, then exp(x - max)
+  float *tile = bsm + m.D * kBwdPix;         // [Cpad][65] context in, g_ctx out
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int frame_chunk = b * m.nchunks + chunk;
+  const int tid = threadIdx.x;
+  const int p0 = ci * kChunk + half * kBwdPix;
+  if (p0 >= m.P) return;  // second half of a ragged last chunk (block-uniform)
+  const int npx = min(kBwdPix, m.P - p0);
+  const int bn = b * m.Nc + n;
+
+  // ---- 1. stage ------------------------------------------------------------------------------------
+  {
+    const int t = tid & (kBwdPix - 1), q = tid >> 6;  // 4 quarter-blocks of threads, each walks a share of the rows
+    if (t < npx) {
+      const float *hs = height + (size_t)bn * m.hs + p0 + t;
+      for (int d = q; d < m.D; d += 4) cp_async_4(col + d * kBwdPix + t, hs + (size_t)d * m.P);
+      const CT *cs = context + (size_t)bn * m.cs + p0 + t;
+      if (sizeof(CT) == 4) {
+        for (int c = q; c < m.C; c += 4)
+          cp_async_4(tile + c * kBwdLd + t, reinterpret_cast<const float *>(cs) + (size_t)c * m.P);
+      } else {
+        for (int c = q; c < m.C; c += 4) tile[c * kBwdLd + t] = to_f32<CT>(cs[(size_t)c * m.P]);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+  }
+
+  const int px = tid >> 2, l = tid & 3;       // group = pixel, lane inside the group
+  const bool live = px < npx;
+  const int tch = half * kBwdPix + px;        // thread index of this pixel inside the plan chunk
+  const int cnt = live ? run_cnt[(size_t)frame_chunk * kChunk + tch] : 0;
+
+  // ---- 2. softmax over D -----------------------------------------------------------------------------
+  float scale = 1.0f;
+  if (m.logits) {
+    float mx = -INFINITY;
+    if (live)
+      for (int d = l; d < m.D; d += 4) mx = fmaxf(mx, col[d * kBwdPix + px]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sm = 0.0f;
+    if (live)
+      for (int d = l; d < m.D; d += 4) {
+        const float e = expf(__fsub_rn(col[d * kBwdPix + px], mx));
+        col[d * kBwdPix + px] = e;
+        sm = __fadd_rn(sm, e);
+      }
+    sm = __fadd_rn(sm, __shfl_xor_sync(0xffffffffu, sm, 1));   // (s0 + s1), (s2 + s3)
+    sm = __fadd_rn(sm, __shfl_xor_sync(0xffffffffu, sm, 2));   // (s0 + s1) + (s2 + s3)
+    scale = __fdiv_rn(1.0f, sm);
+  }
+  // context row of the pixel -> registers (channel l + 4j)
+  float cx[NJ], acc[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c = l + 4 * j;
+    cx[j] = (live && c < m.C) ? tile[c * kBwdLd + px] : 0.0f;
+    acc[j] = 0.0f;
+  }
+  __syncthreads();  // every thread has its context row (and the exponentials are visible to the group)
+
+  // ---- 3a. run weights: lane l takes the runs r = l mod 4 (ascending d inside a run) ----------------------
+  const size_t ell0 = ell_slot(frame_chunk, m.D, 0, tch);
+  for (int r = l; r < cnt; r += 4) {
+    const size_t sl = ell0 + (size_t)r * kChunk;
+    const int packed = run_d[sl];
+    const int d0 = packed & 0xffff, d1 = packed >> 16;
+    float wr = 0.0f;
+    for (int d = d0; d < d1; ++d) wr = __fadd_rn(wr, col[d * kBwdPix + px]);
+    w_pm[sl] = m.logits ? __fmul_rn(wr, scale) : wr;
+  }
+  __syncthreads();  // every lane of the group reads all of the pixel's weights below
+
+  // ---- 3b. runs --------------------------------------------------------------------------------------
+  // Run descriptors are fetched four ahead and two gradient rows are in flight per group, so that the
+  // descriptor -> row dependency and the row latency overlap with the arithmetic of earlier runs.
+  // The trip count is warp-uniform (longest pixel of the warp) so that the butterflies use the full mask.
+  const float *gb = gT + (size_t)b * m.V * kRowF + 4 * l;
+  const int cnt_w = __reduce_max_sync(0xffffffffu, cnt);
+  float S = 0.0f;
+  auto load_g = [&](int vox, float (&g)[NV][4]) {
+    const float *grow = gb + (size_t)vox * kRowF;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4 *>(grow + 16 * k));
+      g[k][0] = t4.x; g[k][1] = t4.y; g[k][2] = t4.z; g[k][3] = t4.w;
+    }
+  };
+  auto consume = [&](int r, float wr, const float (&g)[NV][4]) {
+    float dot = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      fma2(acc[4 * k + 0], acc[4 * k + 1], wr, g[k][0], g[k][1]);
+      fma2(acc[4 * k + 2], acc[4 * k + 3], wr, g[k][2], g[k][3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dot = __fmaf_rn(cx[4 * k + e], g[k][e], dot);
+    }
+    dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 1));
+    dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 2));
+    if (l == 0 && r < cnt) gw_pm[ell0 + (size_t)r * kChunk] = dot;
+    S = __fmaf_rn(wr, dot, S);   // wr == 0 beyond the pixel's last run
+  };
+  for (int r0 = 0; r0 < cnt_w; r0 += 4) {
+    int vox[4];
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vox[u] = 0; wv[u] = 0.0f;
+      if (r0 + u < cnt) {
+        const size_t sl = ell0 + (size_t)(r0 + u) * kChunk;
+        vox[u] = run_vox[sl];
+        wv[u] = w_pm[sl];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+      if (r0 + h < cnt_w) {  // warp-uniform
+        float ga[NV][4], gb2[NV][4];
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { ga[k][e] = 0.0f; gb2[k][e] = 0.0f; }
+        if (r0 + h < cnt) load_g(vox[h], ga);
+        if (r0 + h + 1 < cnt) load_g(vox[h + 1], gb2);
+        consume(r0 + h, wv[h], ga);
+        consume(r0 + h + 1, wv[h + 1], gb2);
+      }
+    }
+  }
+  // g_ctx row -> tile column (the context values are in registers now)
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = l + 4 * j;
+      if (c < m.C) tile[c * kBwdLd + px] = acc[j];
+    }
+  }
+  __syncthreads();  // tile complete; gw_pm writes of this CTA are visible to it
+
+  // ---- 4a. g_height: lane l writes the bins d = l mod 4 ------------------------------------------------
+  if (live) {
+    float *gh = g_height + (size_t)bn * m.ghs + p0 + px;
+    auto put = [&](int d, float gv) {
+      float v = gv;
+      if (m.logits) v = __fmul_rn(__fmul_rn(col[d * kBwdPix + px], scale), __fsub_rn(gv, S));
+      stg_stream_f1(gh + (size_t)d * m.P, v);
+    };
+    int dc = l;  // next bin of this lane
+    for (int r = 0; r < cnt; ++r) {
+      const size_t sl = ell0 + (size_t)r * kChunk;
+      const int packed = run_d[sl];
+      const float gv = gw_pm[sl];
+      const int d0 = packed & 0xffff, d1 = packed >> 16;
+      for (; dc < d0; dc += 4) put(dc, 0.0f);
+      for (; dc < d1; dc += 4) put(dc, gv);
+    }
+    for (; dc < m.D; dc += 4) put(dc, 0.0f);
+  }
+  // ---- 4b. g_ctx tile -> NCHW rows (256-byte segments) ------------------------------------------------
+  {
+    const int t = tid & (kBwdPix - 1), q = tid >> 6;
+    if (t < npx) {
+      float *gc = g_context + (size_t)bn * m.gcs + p0 + t;
+      for (int c = q; c < m.C; c += 4) stg_stream_f1(gc + (size_t)c * m.P, tile[c * kBwdLd + t]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // g_height[d, pixel] = gw[run containing d], 0 for dropped bins; thread per pixel, coalesced rows.
 // MODE 0: plain.  MODE 1: softmax backward fused (height holds logits):
 //   g_logit[d] = p[d] * (g_p[d] - sum_d' p[d'] g_p[d'])   with  sum_d' p g_p = sum_runs w_run * gw_run.
@@ -1319,6 +1558,31 @@ int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s)
   return launch_reduce_cfg<CT, 16, 4, 16>(m, w, bev, s);
 }
 
+template <typename CT, int NV>
+int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *height, const void *context,
+                              float *grad_height, float *grad_context, cudaStream_t s) {
+  const size_t smem = sizeof(float) * ((size_t)m.D * kBwdPix + (size_t)m.Cpad * kBwdLd);
+  if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV>, smem)) return rc;
+  ls_backward_chunk_kernel<CT, NV><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(
+      m, height, static_cast<const CT *>(context), w.gT, w.run_cnt, w.run_vox, w.run_d, w.w_pm, w.gw_pm,
+      grad_height, grad_context);
+  SGV3D_CHECK_LAUNCH("ls_backward_chunk_kernel");
+  return SGV3D_OK;
+}
+
+template <typename CT>
+int launch_backward_chunk(const Dims &m, const Workspace &w, const float *height, const void *context,
+                          float *grad_height, float *grad_context, cudaStream_t s) {
+  switch (m.NV) {
+    case 1: return launch_backward_chunk_cfg<CT, 1>(m, w, height, context, grad_height, grad_context, s);
+    case 2: return launch_backward_chunk_cfg<CT, 2>(m, w, height, context, grad_height, grad_context, s);
+    case 3: return launch_backward_chunk_cfg<CT, 3>(m, w, height, context, grad_height, grad_context, s);
+    case 4: return launch_backward_chunk_cfg<CT, 4>(m, w, height, context, grad_height, grad_context, s);
+    case 5: return launch_backward_chunk_cfg<CT, 5>(m, w, height, context, grad_height, grad_context, s);
+    default: return launch_backward_chunk_cfg<CT, 6>(m, w, height, context, grad_height, grad_context, s);
+  }
+}
+
 template <typename CT>
 int launch_backward_gather(const Dims &m, const Workspace &w, int gpad, cudaStream_t s) {
   dim3 grid(ceil_div(m.Nc * m.P, 8), m.B);
@@ -1449,6 +1713,16 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   const int gpad = m.Cpad;  // gradient rows share the context rows' (permuted) channel layout
+  if (m.G == 4) {
+    // fused path: grad_bev -> one row per voxel, then everything else per pixel chunk in one kernel
+    const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
+    if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
+    ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
+    SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
+    return desc->ctx_dtype == SGV3D_DTYPE_BF16
+               ? launch_backward_chunk<__nv_bfloat16>(m, w, height, context, grad_height, grad_context, s)
+               : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s);
+  }
   if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, false, s)) return rc;
   launch_transpose_pad<float, float, 1>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
                                         (size_t)m.V * gpad, s, row_perm(m));
