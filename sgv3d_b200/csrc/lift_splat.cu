@@ -532,8 +532,7 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
 // (pixel row | voxel-in-tile) and the inverse permutation run_dst (ELL slot -> sorted position) that the
 // forward weights pass scatters through.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFinWarps = 4;
-
+template <int kFinWarps>
 __global__ void __launch_bounds__(kFinWarps * 32)
 ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt *__restrict__ bucket,
                        Entry *__restrict__ vm_ent, int *__restrict__ run_dst) {
@@ -815,7 +814,8 @@ struct RowLoad<__nv_bfloat16> {
 
 // ---- reduce: tile geometry ----------------------------------------------------------------------
 constexpr int kTileV = 64;     // voxels per reduce CTA: two 32-voxel boxes = 2 x 128-byte rows per channel
-constexpr int kStageE = 1536;  // entries staged in shared memory (larger tiles read them from global)
+// Entries of a tile are staged in shared memory when they fit (stage_cap, chosen per launch from the
+// expected tile population); larger tiles read them from the plan in global memory.
 static_assert(kTileV == 64, "Entry::off carries the voxel-in-tile index in its low 6 bits");
 
 // 4-element row vector widened to fp32 (byte address).
@@ -981,14 +981,14 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
 template <typename CT, int G, int NV, int NSTR>
 __global__ void __launch_bounds__(NSTR * G)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ tile_ptr,
-                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out) {
+                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out, int stage_cap) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int kThreads = NSTR * G;
   constexpr int kRows = 4 * G * NV;                  // = Cpad rows (rows >= C are scratch)
   constexpr unsigned kBoxBytes = kRows * 128;
   unsigned char *tile = smem_raw;                                          // 2 boxes x kRows x 128 B
   float *s_head = reinterpret_cast<float *>(smem_raw + 2 * kBoxBytes);     // NSTR x kRows partial sums
-  Entry *s_ent = reinterpret_cast<Entry *>(s_head + NSTR * kRows);         // kStageE entries
+  Entry *s_ent = reinterpret_cast<Entry *>(s_head + NSTR * kRows);         // stage_cap entries
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int l = tid & (G - 1);
@@ -1020,7 +1020,7 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
   }
 
   const int n_t = tile_hi - tile_lo;
-  const bool staged = n_t <= kStageE;
+  const bool staged = n_t <= stage_cap;
   const Entry *ent = vm_ent + (size_t)b * m.cap;
   if (staged)
     for (int i = tid; i < n_t; i += kThreads) cp_async_8(s_ent + i, ent + tile_lo + i);
@@ -1526,12 +1526,17 @@ int set_smem(K kernel, size_t bytes) {
 template <typename CT, int G, int NV, int NSTR>
 int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
   dim3 grid(ceil_div(m.V, kTileV), m.B);
-  const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * kStageE;
+  // expected entries per touched tile ~ pixels * (runs per pixel ~ 25) / (touched tiles ~ 170 per 128 x 128
+  // grid); stage up to ~2x that, within 1.5 K .. 6 K entries (12 .. 48 KB)
+  long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
+  int stage_cap = 1536;
+  while (stage_cap < 2 * expect && stage_cap < 6144) stage_cap += 1536;
+  const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * stage_cap;
   if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR>, smem)) return rc;
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
   ls_reduce_kernel<CT, G, NV, NSTR><<<grid, NSTR * G, smem, s>>>(
-      m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out);
+      m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
 }
@@ -1677,8 +1682,11 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   if (int rc = set_smem(ls_scatter_tiles_kernel, csm)) return rc;
   ls_scatter_tiles_kernel<<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
   SGV3D_CHECK_LAUNCH("ls_scatter_tiles_kernel");
-  ls_finish_tiles_kernel<<<dim3(m.ntiles, m.B), kFinWarps * 32, 0, s>>>(
-      m, w.tile_ptr, w.bucket, w.vm_ent, w.run_dst);
+  // heavy tiles (dense feature maps) get more warps: the kernel's tail is its most populated tile
+  if ((long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1) > 1024)
+    ls_finish_tiles_kernel<16><<<dim3(m.ntiles, m.B), 16 * 32, 0, s>>>(m, w.tile_ptr, w.bucket, w.vm_ent, w.run_dst);
+  else
+    ls_finish_tiles_kernel<4><<<dim3(m.ntiles, m.B), 4 * 32, 0, s>>>(m, w.tile_ptr, w.bucket, w.vm_ent, w.run_dst);
   SGV3D_CHECK_LAUNCH("ls_finish_tiles_kernel");
   return SGV3D_OK;
 }
