@@ -463,15 +463,17 @@ constexpr int kScatRows = 64;
 struct EllInput {
   const int *keys_s;   // shared: [kScatRows][kChunk]
   const int *run_vox;  // global ELL table
-  int frame_chunk, chunk, D;
+  int frame_chunk, D;
   int cnt;     // runs of this thread's pixel
   int warp_max;
   __device__ __forceinline__ int iters(int) const { return warp_max; }
+  // key = voxel id of run `it` of this thread's pixel; payload = the run index (each thread loads and places
+  // only its own pixel's runs, so everything else about the run is thread-local state of the placer)
   __device__ __forceinline__ bool load(int w, int it, int lane, int &key, int &pay) const {
     if (it >= cnt) return false;
     const int t = w * 32 + lane;
     key = it < kScatRows ? keys_s[it * kChunk + t] : run_vox[ell_slot(frame_chunk, D, it, t)];
-    pay = (chunk * D + it) * kChunk + t;
+    pay = it;
     return true;
   }
 };
@@ -485,14 +487,12 @@ struct TileBase {
 };
 struct PlaceBucket {
   BucketEnt *bucket;
-  int D, cpc, P;
-  __device__ __forceinline__ void operator()(int pos, int vox, int slot) const {
-    const int t = slot & (kChunk - 1);
-    const int chunk = (slot / kChunk) / D;
-    const int n = chunk / cpc, ci = chunk - n * cpc;
+  unsigned row6;   // this thread's frame-local pixel row (n*P + p) << 6
+  int slot0;       // frame-local ELL slot of this pixel's run 0; run r sits kChunk further per run
+  __device__ __forceinline__ void operator()(int pos, int vox, int run) const {
     BucketEnt e;
-    e.key = ((unsigned)(n * P + ci * kChunk + t) << 6) | (unsigned)(vox & 63);
-    e.slot = slot;
+    e.key = row6 | (unsigned)(vox & 63);
+    e.slot = slot0 + run * kChunk;
     bucket[pos] = e;
   }
 };
@@ -509,7 +509,6 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
   in.keys_s = keys_s;
   in.run_vox = run_vox;
   in.frame_chunk = frame_chunk;
-  in.chunk = chunk;
   in.D = m.D;
   in.cnt = run_cnt[(size_t)frame_chunk * kChunk + threadIdx.x];
   in.warp_max = __reduce_max_sync(0xffffffffu, in.cnt);
@@ -524,7 +523,9 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
   sort::stable_scatter_block<kChunk / 32>(
       in, TileOf(), m.ntiles,
       TileBase{tile_ptr + (size_t)b * (m.ntiles + 1), hist + (size_t)frame_chunk * m.ntiles}, s_cnt,
-      PlaceBucket{bucket + (size_t)b * m.cap, m.D, m.cpc, m.P});
+      PlaceBucket{bucket + (size_t)b * m.cap,
+                  (unsigned)((chunk / m.cpc) * m.P + (chunk % m.cpc) * kChunk + (int)threadIdx.x) << 6,
+                  chunk * m.D * kChunk + (int)threadIdx.x});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -615,15 +616,17 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_columns(float *col, const float *__restrict__ src /*camera base*/,
                                               int D, int P, int p0, bool vec16) {
-  const int t = threadIdx.x;
+  const int tid = threadIdx.x;
   const int npx = min(kChunk, P - p0);
   if (vec16 && npx == kChunk) {
     // one warp copies one 512-byte row per instruction
-    const int lane = t & 31, wid = t >> 5;
-    for (int d = wid; d < D; d += kChunk / 32)
+    const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    for (int d = wid; d < D; d += nw)
       cp_async_16(col + d * kChunk + lane * 4, src + (size_t)d * P + p0 + lane * 4);
-  } else if (t < npx) {
-    for (int d = 0; d < D; ++d) cp_async_4(col + d * kChunk + t, src + (size_t)d * P + p0 + t);
+  } else {
+    const int t = tid & (kChunk - 1), q = tid / kChunk, nq = blockDim.x / kChunk;
+    if (t < npx)
+      for (int d = q; d < D; d += nq) cp_async_4(col + d * kChunk + t, src + (size_t)d * P + p0 + t);
   }
   cp_async_wait_all();
   __syncthreads();
@@ -667,67 +670,106 @@ __device__ __forceinline__ float softmax_column(float *col, int D, int t) {
 // pixel-major (ELL slot of the run; coalesced).  The forward reduce gathers them through the slot
 // index its sorted entries carry.
 // ---------------------------------------------------------------------------------------------
+constexpr int kPrepThreads = 2 * kChunk;  // two threads per pixel column (halves of D, alternate runs)
+
+// Partial softmax statistics of one half-column: max, then exp(x - m) in place and its sum.
+// Four independent chains over d = lo + 4i + k (fixed interleaving => deterministic).
+__device__ __forceinline__ float column_max(const float *col, int lo, int hi, int t) {
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int d = lo;
+  for (; d + 4 <= hi; d += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mx[k] = fmaxf(mx[k], col[(d + k) * kChunk + t]);
+  }
+  for (; d < hi; ++d) mx[0] = fmaxf(mx[0], col[d * kChunk + t]);
+  return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+}
+__device__ __forceinline__ float column_exp_sum(float *col, int lo, int hi, int t, float m) {
+  float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  int d = lo;
+  for (; d + 4 <= hi; d += 4) {
+    float e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = expf(__fsub_rn(col[(d + k) * kChunk + t], m));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      col[(d + k) * kChunk + t] = e[k];
+      s[k] = __fadd_rn(s[k], e[k]);
+    }
+  }
+  for (; d < hi; ++d) {
+    const float e = expf(__fsub_rn(col[d * kChunk + t], m));
+    col[d * kChunk + t] = e;
+    s[0] = __fadd_rn(s[0], e);
+  }
+  return __fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3]));
+}
+
 // vm_ent_out != nullptr: forward, the weight goes to the run's voxel-major entry (through run_dst);
-// else backward, pixel-major w_pm_out.
+// else backward (unfused path), pixel-major w_pm_out.  256 threads: thread (t, h) owns half h of pixel t's
+// column for the softmax statistics and the runs r = h mod 2.
 __device__ __forceinline__ void weights_role(const Dims &m, const float *__restrict__ height, int vec16,
                                              const int *__restrict__ run_cnt, const int *__restrict__ run_d,
                                              const int *__restrict__ run_dst, float *__restrict__ w_pm_out,
                                              Entry *__restrict__ vm_ent_out, float *col, int b, int chunk) {
+  __shared__ float s_max[2][kChunk], s_sum[2][kChunk];
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x & (kChunk - 1), h = threadIdx.x / kChunk;
   const int p0 = ci * kChunk;
   stage_columns(col, height + (size_t)(b * m.Nc + n) * m.hs, m.D, m.P, p0, vec16 != 0);
-  if (p0 + t >= m.P) return;
-  const int cnt = run_cnt[(size_t)frame_chunk * kChunk + t];
-  if (cnt == 0) return;
+  const bool live = p0 + t < m.P;
+  const int cnt = live ? run_cnt[(size_t)frame_chunk * kChunk + t] : 0;
   // the first run descriptors are requested before the softmax so that their latency hides behind it
-  constexpr int kPre = 8;
+  constexpr int kPre = 6;
   int pre_d[kPre], pre_dst[kPre];
 #pragma unroll
   for (int u = 0; u < kPre; ++u) {
     pre_d[u] = 0; pre_dst[u] = 0;
-    if (u < cnt) {
-      const size_t sl = ell_slot(frame_chunk, m.D, u, t);
+    const int r = h + 2 * u;
+    if (r < cnt) {
+      const size_t sl = ell_slot(frame_chunk, m.D, r, t);
       pre_d[u] = run_d[sl];
       if (vm_ent_out) pre_dst[u] = run_dst[sl];
     }
   }
-  const float scale = m.logits ? softmax_column(col, m.D, t) : 1.0f;
-#pragma unroll
-  for (int u = 0; u < kPre; ++u) {
-    if (u < cnt) {
-      const int d0 = pre_d[u] & 0xffff, d1 = pre_d[u] >> 16;
-      float acc = 0.0f;
-      for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-      const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
-      if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + pre_dst[u]].w = wgt;
-      else w_pm_out[ell_slot(frame_chunk, m.D, u, t)] = wgt;
-    }
+  float scale = 1.0f;
+  if (m.logits) {  // block-uniform
+    const int half = (m.D + 1) >> 1;
+    const int lo = h * half, hi = min(m.D, lo + half);
+    s_max[h][t] = (live && cnt > 0) ? column_max(col, lo, hi, t) : 0.0f;
+    __syncthreads();
+    const float mx = fmaxf(s_max[0][t], s_max[1][t]);
+    s_sum[h][t] = (live && cnt > 0) ? column_exp_sum(col, lo, hi, t, mx) : 1.0f;
+    __syncthreads();  // both halves of every column now hold exp(x - max)
+    scale = __fdiv_rn(1.0f, __fadd_rn(s_sum[0][t], s_sum[1][t]));
   }
+  auto emit = [&](int r, int packed, int dst) {
+    const int d0 = packed & 0xffff, d1 = packed >> 16;
+    float acc = 0.0f;
+    for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
+    const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
+    if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + dst].w = wgt;
+    else w_pm_out[ell_slot(frame_chunk, m.D, r, t)] = wgt;
+  };
+#pragma unroll
+  for (int u = 0; u < kPre; ++u)
+    if (h + 2 * u < cnt) emit(h + 2 * u, pre_d[u], pre_dst[u]);
   // the rest in batches of 4 (strided descriptors)
-  for (int r0 = kPre; r0 < cnt; r0 += 4) {
+  for (int r0 = h + 2 * kPre; r0 < cnt; r0 += 8) {
     int packed[4], dst[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       packed[u] = 0; dst[u] = 0;
-      if (r0 + u < cnt) {
-        const size_t sl = ell_slot(frame_chunk, m.D, r0 + u, t);
+      if (r0 + 2 * u < cnt) {
+        const size_t sl = ell_slot(frame_chunk, m.D, r0 + 2 * u, t);
         packed[u] = run_d[sl];
         if (vm_ent_out) dst[u] = run_dst[sl];
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (r0 + u < cnt) {
-        const int d0 = packed[u] & 0xffff, d1 = packed[u] >> 16;
-        float acc = 0.0f;
-        for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-        const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
-        if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + dst[u]].w = wgt;
-        else w_pm_out[ell_slot(frame_chunk, m.D, r0 + u, t)] = wgt;
-      }
-    }
+    for (int u = 0; u < 4; ++u)
+      if (r0 + 2 * u < cnt) emit(r0 + 2 * u, packed[u], dst[u]);
   }
 }
 
@@ -740,19 +782,22 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
                                                   CT *__restrict__ ctxT, RowPerm perm, float *smem, int b,
                                                   int chunk) {
   constexpr int kLd = kChunk + 1;
+  constexpr int kWarps = kPrepThreads / 32, kQ = kPrepThreads / kChunk;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int t = threadIdx.x & (kChunk - 1), q = threadIdx.x / kChunk;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int p0 = ci * kChunk;
   const int npx = min(kChunk, m.P - p0);
-  const CT *src = context + (size_t)(b * m.Nc + n) * m.cs + p0 + t;
+  const CT *src = context + (size_t)(b * m.Nc + n) * m.cs + p0 + t + (size_t)q * m.P;
   if (t < npx) {
-    float *sp = smem + t;
+    float *sp = smem + q * kLd + t;
     if (sizeof(CT) == 4) {
 #pragma unroll 4
-      for (int c = 0; c < m.C; ++c, sp += kLd, src += m.P) cp_async_4(sp, reinterpret_cast<const float *>(src));
+      for (int c = q; c < m.C; c += kQ, sp += kQ * kLd, src += (size_t)kQ * m.P)
+        cp_async_4(sp, reinterpret_cast<const float *>(src));
     } else {
 #pragma unroll 4
-      for (int c = 0; c < m.C; ++c, sp += kLd, src += m.P) *sp = to_f32<CT>(*src);
+      for (int c = q; c < m.C; c += kQ, sp += kQ * kLd, src += (size_t)kQ * m.P) *sp = to_f32<CT>(*src);
     }
   }
   cp_async_wait_all();
@@ -765,13 +810,13 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
     if (e >= m.Cpad) continue;
     const int c = perm.chan(e);
     CT *dp = dst + (size_t)wid * m.Cpad + e;
-    const size_t dstep = (size_t)(kChunk / 32) * m.Cpad;
+    const size_t dstep = (size_t)kWarps * m.Cpad;
     if (c < m.C) {
       const float *sp = smem + c * kLd + wid;
 #pragma unroll 4
-      for (int px = wid; px < npx; px += kChunk / 32, sp += kChunk / 32, dp += dstep) *dp = from_f32<CT>(*sp);
+      for (int px = wid; px < npx; px += kWarps, sp += kWarps, dp += dstep) *dp = from_f32<CT>(*sp);
     } else {
-      for (int px = wid; px < npx; px += kChunk / 32, dp += dstep) *dp = from_f32<CT>(0.0f);
+      for (int px = wid; px < npx; px += kWarps, dp += dstep) *dp = from_f32<CT>(0.0f);
     }
   }
 }
@@ -779,7 +824,7 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
 // One launch, two kinds of CTA (blockIdx.z): run weights of a pixel chunk (ALU / latency bound) and
 // channels-last context rows of a pixel chunk (bandwidth bound) -- they overlap on every SM.
 template <typename CT>
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kPrepThreads)
 ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
                     const int *__restrict__ run_d, const int *__restrict__ run_dst,
                     float *__restrict__ w_pm_out, Entry *__restrict__ vm_ent_out,
@@ -1612,12 +1657,12 @@ int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const flo
   const int vec16 = columns_vec16(height, m.hs, m.P) ? 1 : 0;
   if (ctx_dtype == SGV3D_DTYPE_BF16) {
     if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16>, smem2)) return rc;
-    ls_lift_prep_kernel<__nv_bfloat16><<<grid, kChunk, smem2, s>>>(
+    ls_lift_prep_kernel<__nv_bfloat16><<<grid, kPrepThreads, smem2, s>>>(
         m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm, vm_out, static_cast<const __nv_bfloat16 *>(context),
         static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m));
   } else {
     if (int rc = set_smem(ls_lift_prep_kernel<float>, smem2)) return rc;
-    ls_lift_prep_kernel<float><<<grid, kChunk, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
+    ls_lift_prep_kernel<float><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
                                                           vm_out, static_cast<const float *>(context),
                                                           static_cast<float *>(w.ctxT), row_perm(m));
   }
