@@ -33,6 +33,10 @@
 //
 // No floating-point atomics anywhere; every sum has a fixed order => bitwise reproducible.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <stdlib.h>
 
 #include "geometry.cuh"
 #include "sort.cuh"
@@ -85,8 +89,7 @@ struct Workspace {
 // Row layout by channel count: a G-lane group owns a whole channels-last row, NV 4-element vectors per
 // lane (Cpad = 4*G*NV = 16*G*NV bytes in fp32: rows start on 64-byte boundaries, no padding at C = 80).
 void pick_row_cfg(int C, int *G, int *NV) {
-  if (C <= 96) { *G = 4; *NV = ceil_div(C, 16); }
-  else if (C <= 192) { *G = 8; *NV = ceil_div(C, 32); }
+  if (C <= 192) { *G = 8; *NV = ceil_div(C, 32); }
   else { *G = 16; *NV = ceil_div(C, 64); }
 }
 
@@ -175,8 +178,18 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
   __shared__ geom::Camera cam;
   extern __shared__ float z_s[];                           // [D] height-bin values, then
   int *s_hist = reinterpret_cast<int *>(z_s + m.D);        // [ntiles] runs per reduce tile
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  if (chunk_done[b * m.nchunks + chunk]) return;  // the fast kernel already produced this chunk
+  // Persistent grid over the (frame, chunk) list: normally the fast kernel has produced every chunk, so the
+  // whole launch is one bulk look at the flags (a full-size grid of early exits costs ~6 us per step).
+  const int total = m.nchunks * m.B;
+  {
+    int todo = 0;
+    for (int i = blockIdx.x + (int)threadIdx.x * (int)gridDim.x; i < total; i += (int)gridDim.x * kChunk)
+      todo |= (chunk_done[i] == 0);
+    if (!__syncthreads_or(todo)) return;
+  }
+  for (int fc = blockIdx.x; fc < total; fc += gridDim.x) {
+  if (chunk_done[fc]) continue;  // the fast kernel already produced this chunk (block-uniform)
+  const int b = fc / m.nchunks, chunk = fc - b * m.nchunks;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int bn = b * m.Nc + n;
   const int t = threadIdx.x;
@@ -222,6 +235,8 @@ ls_plan_runs_kernel(Dims m, const float *__restrict__ u_tab, const float *__rest
   __syncthreads();
   int *hh = hist + (size_t)frame_chunk * m.ntiles;
   for (int i = t; i < m.ntiles; i += kChunk) hh[i] = s_hist[i];
+  __syncthreads();  // cam / z_s / s_hist are rewritten by the next chunk
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -497,12 +512,25 @@ struct PlaceBucket {
   }
 };
 
+struct SmemBase {
+  const int *base;
+  __device__ __forceinline__ int operator()(int tile) const { return base[tile]; }
+};
+
+// FUSED: the scan of ls_scan_tiles_kernel is done here, redundantly per CTA, straight from the raw per-chunk
+// histograms (small grids: nchunks * ntiles ints stay L2-resident and a CTA reads them in ~1 us, less than the
+// separate single-CTA-per-frame scan kernel and its launch cost).  The CTA of chunk 0 publishes tile_ptr.
+constexpr int kFusedScanMaxTiles = 1024, kFusedScanMaxCells = 16384;
+
+template <bool FUSED>
 __global__ void __launch_bounds__(kChunk)
 ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__restrict__ run_vox,
-                        const int *__restrict__ hist, const int *__restrict__ tile_ptr,
+                        const int *__restrict__ hist, int *__restrict__ tile_ptr,
                         BucketEnt *__restrict__ bucket) {
-  extern __shared__ int s_cnt[];  // [kChunk / 32][ntiles], then the staged keys [kScatRows][kChunk]
+  extern __shared__ int s_cnt[];  // [kChunk / 32][ntiles], then the staged keys [kScatRows][kChunk], then [ntiles] bases
   int *keys_s = s_cnt + (kChunk / 32) * m.ntiles;
+  int *s_base = keys_s + kScatRows * kChunk;
+  __shared__ int s_wtot[kChunk / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int frame_chunk = b * m.nchunks + chunk;
   EllInput in;
@@ -513,19 +541,78 @@ ls_scatter_tiles_kernel(Dims m, const int *__restrict__ run_cnt, const int *__re
   in.cnt = run_cnt[(size_t)frame_chunk * kChunk + threadIdx.x];
   in.warp_max = __reduce_max_sync(0xffffffffu, in.cnt);
   // every key of the chunk in flight at once (one round trip instead of one per batch of runs)
-  {
-    const int nst = min(in.cnt, kScatRows);
-    for (int r = 0; r < nst; ++r)
-      cp_async_4(reinterpret_cast<float *>(keys_s + r * kChunk + threadIdx.x),
-                 reinterpret_cast<const float *>(run_vox + ell_slot(frame_chunk, m.D, r, threadIdx.x)));
-    cp_async_wait_all();  // each thread reads back only what it copied itself
+  const int nst = min(in.cnt, kScatRows);
+  for (int r = 0; r < nst; ++r)
+    cp_async_4(reinterpret_cast<float *>(keys_s + r * kChunk + threadIdx.x),
+               reinterpret_cast<const float *>(run_vox + ell_slot(frame_chunk, m.D, r, threadIdx.x)));
+  if (FUSED) {
+    constexpr int kTpt = kFusedScanMaxTiles / kChunk;  // tiles per thread, at most
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int tpt = (m.ntiles + kChunk - 1) / kChunk;
+    const int t0 = t * tpt;
+    const int *h = hist + (size_t)b * m.nchunks * m.ntiles;
+    int pre[kTpt], tot[kTpt];
+#pragma unroll
+    for (int k = 0; k < kTpt; ++k) { pre[k] = 0; tot[k] = 0; }
+    auto sweep = [&](int c_lo, int c_hi, int (&acc)[kTpt]) {
+      int c = c_lo;
+      for (; c + 4 <= c_hi; c += 4) {
+        int v[4][kTpt];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < kTpt; ++k)
+            v[u][k] = (k < tpt && t0 + k < m.ntiles) ? __ldg(h + (size_t)(c + u) * m.ntiles + t0 + k) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < kTpt; ++k) acc[k] += v[u][k];
+      }
+      for (; c < c_hi; ++c)
+#pragma unroll
+        for (int k = 0; k < kTpt; ++k)
+          if (k < tpt && t0 + k < m.ntiles) acc[k] += __ldg(h + (size_t)c * m.ntiles + t0 + k);
+    };
+    sweep(0, chunk, pre);            // runs of each tile in the chunks before this one
+    sweep(chunk, m.nchunks, tot);
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kTpt; ++k) { tot[k] += pre[k]; sum += tot[k]; }
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_wtot[wid] = x;
+    __syncthreads();
+    int excl = x - sum;
+    for (int w = 0; w < wid; ++w) excl += s_wtot[w];
+    int *tp = tile_ptr + (size_t)b * (m.ntiles + 1);
+#pragma unroll
+    for (int k = 0; k < kTpt; ++k) {
+      if (k < tpt && t0 + k < m.ntiles) {
+        s_base[t0 + k] = excl + pre[k];
+        if (chunk == 0) tp[t0 + k] = excl;
+      }
+      excl += tot[k];
+    }
+    if (chunk == 0 && t == kChunk - 1) tp[m.ntiles] = excl;  // runs of the frame
   }
-  sort::stable_scatter_block<kChunk / 32>(
-      in, TileOf(), m.ntiles,
-      TileBase{tile_ptr + (size_t)b * (m.ntiles + 1), hist + (size_t)frame_chunk * m.ntiles}, s_cnt,
-      PlaceBucket{bucket + (size_t)b * m.cap,
-                  (unsigned)((chunk / m.cpc) * m.P + (chunk % m.cpc) * kChunk + (int)threadIdx.x) << 6,
-                  chunk * m.D * kChunk + (int)threadIdx.x});
+  cp_async_wait_all();  // each thread reads back only what it copied itself
+  if (FUSED)
+    sort::stable_scatter_block<kChunk / 32>(
+        in, TileOf(), m.ntiles, SmemBase{s_base}, s_cnt,
+        PlaceBucket{bucket + (size_t)b * m.cap,
+                    (unsigned)((chunk / m.cpc) * m.P + (chunk % m.cpc) * kChunk + (int)threadIdx.x) << 6,
+                    chunk * m.D * kChunk + (int)threadIdx.x});
+  else
+    sort::stable_scatter_block<kChunk / 32>(
+        in, TileOf(), m.ntiles,
+        TileBase{tile_ptr + (size_t)b * (m.ntiles + 1), hist + (size_t)frame_chunk * m.ntiles}, s_cnt,
+        PlaceBucket{bucket + (size_t)b * m.cap,
+                    (unsigned)((chunk / m.cpc) * m.P + (chunk % m.cpc) * kChunk + (int)threadIdx.x) << 6,
+                    chunk * m.D * kChunk + (int)threadIdx.x});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1576,8 +1663,11 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
   int stage_cap = 1536;
   while (stage_cap < 2 * expect && stage_cap < 6144) stage_cap += 1536;
+  if (const char *e = getenv("SGV3D_EXP_STAGE")) stage_cap = atoi(e);
   const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * stage_cap;
   if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR>, smem)) return rc;
+  if (const char *e = getenv("SGV3D_EXP_CARVE"))
+    SGV3D_CUDA(cudaFuncSetAttribute(ls_reduce_kernel<CT, G, NV, NSTR>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
   ls_reduce_kernel<CT, G, NV, NSTR><<<grid, NSTR * G, smem, s>>>(
@@ -1586,23 +1676,28 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   return SGV3D_OK;
 }
 
+template <typename CT, int G, int NV>
+int launch_reduce_nstr(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+  // streams per tile by the expected tile population (pixels * ~25 runs / ~2/3 of the tiles touched): a tile is
+  // one CTA, so the most populated tiles of a dense feature map (stride 8) set the kernel's tail
+  const long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
+  int nstr = expect > 6000 ? 128 : (expect > 1500 ? 64 : 32);
+  if (const char *e = getenv("SGV3D_EXP_NSTR")) nstr = atoi(e);
+  if (nstr == 128) return launch_reduce_cfg<CT, G, NV, 128>(m, w, bev, s);
+  if (nstr == 64) return launch_reduce_cfg<CT, G, NV, 64>(m, w, bev, s);
+  return launch_reduce_cfg<CT, G, NV, 32>(m, w, bev, s);
+}
+
 template <typename CT>
 int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
-  if (m.G == 4) {
-    switch (m.NV) {
-      case 1: return launch_reduce_cfg<CT, 4, 1, 32>(m, w, bev, s);
-      case 2: return launch_reduce_cfg<CT, 4, 2, 32>(m, w, bev, s);
-      case 3: return launch_reduce_cfg<CT, 4, 3, 32>(m, w, bev, s);
-      case 4: return launch_reduce_cfg<CT, 4, 4, 32>(m, w, bev, s);
-      case 5: return launch_reduce_cfg<CT, 4, 5, 32>(m, w, bev, s);
-      default: return launch_reduce_cfg<CT, 4, 6, 32>(m, w, bev, s);
-    }
-  }
   if (m.G == 8) {
     switch (m.NV) {
-      case 4: return launch_reduce_cfg<CT, 8, 4, 32>(m, w, bev, s);
-      case 5: return launch_reduce_cfg<CT, 8, 5, 32>(m, w, bev, s);
-      default: return launch_reduce_cfg<CT, 8, 6, 32>(m, w, bev, s);
+      case 1: return launch_reduce_nstr<CT, 8, 1>(m, w, bev, s);
+      case 2: return launch_reduce_nstr<CT, 8, 2>(m, w, bev, s);
+      case 3: return launch_reduce_nstr<CT, 8, 3>(m, w, bev, s);
+      case 4: return launch_reduce_nstr<CT, 8, 4>(m, w, bev, s);
+      case 5: return launch_reduce_nstr<CT, 8, 5>(m, w, bev, s);
+      default: return launch_reduce_nstr<CT, 8, 6>(m, w, bev, s);
     }
   }
   return launch_reduce_cfg<CT, 16, 4, 16>(m, w, bev, s);
@@ -1670,6 +1765,19 @@ int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const flo
   return SGV3D_OK;
 }
 
+int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, const float *grad_bev,
+                          const float *height, const void *context, float *grad_height, float *grad_context,
+                          cudaStream_t s) {
+  // grad_bev -> one row per voxel, then everything else per pixel chunk in one kernel
+  const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
+  if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
+  ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
+  SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
+  return ctx_dtype == SGV3D_DTYPE_BF16
+             ? launch_backward_chunk<__nv_bfloat16>(m, w, height, context, grad_height, grad_context, s)
+             : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s);
+}
+
 }  // namespace
 }  // namespace sgv3d
 
@@ -1705,6 +1813,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   grid.rcp_size[1] = 1.0f / grid.size[1];
 
   dim3 gc(m.nchunks, m.B);
+  const int gen_grid = std::min(m.nchunks * m.B, 5 * kNumSMs);  // 5 CTAs of the general kernel fit on an SM
   const size_t zsm = sizeof(float) * m.D + sizeof(int) * m.ntiles;
 #define SGV3D_PLAN_RUNS(A)                                                                                  \
   do {                                                                                                      \
@@ -1712,7 +1821,7 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
                                                         bda, ref_heights, grid, w.run_cnt, w.run_vox,       \
                                                         w.run_d, w.hist, w.chunk_done);                     \
     SGV3D_CHECK_LAUNCH("ls_plan_runs_fast_kernel");                                                         \
-    ls_plan_runs_kernel<A><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda,   \
+    ls_plan_runs_kernel<A><<<gen_grid, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda,   \
                                                    ref_heights, grid, w.run_cnt, w.run_vox, w.run_d,        \
                                                    w.hist, w.chunk_done);                                   \
   } while (0)
@@ -1721,11 +1830,16 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   else SGV3D_PLAN_RUNS(SGV3D_ARITH_SEQ);
 #undef SGV3D_PLAN_RUNS
   SGV3D_CHECK_LAUNCH("ls_plan_runs_kernel");
-  ls_scan_tiles_kernel<<<m.B, kScanThreads, 0, s>>>(m, w.hist, w.tile_ptr);
-  SGV3D_CHECK_LAUNCH("ls_scan_tiles_kernel");
-  const size_t csm = sizeof(int) * ((kChunk / 32) * m.ntiles + kScatRows * kChunk);
-  if (int rc = set_smem(ls_scatter_tiles_kernel, csm)) return rc;
-  ls_scatter_tiles_kernel<<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
+  const size_t csm = sizeof(int) * ((kChunk / 32) * m.ntiles + kScatRows * kChunk + m.ntiles);
+  if (m.ntiles <= kFusedScanMaxTiles && m.nchunks * m.ntiles <= kFusedScanMaxCells) {
+    if (int rc = set_smem(ls_scatter_tiles_kernel<true>, csm)) return rc;
+    ls_scatter_tiles_kernel<true><<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
+  } else {
+    ls_scan_tiles_kernel<<<m.B, kScanThreads, 0, s>>>(m, w.hist, w.tile_ptr);
+    SGV3D_CHECK_LAUNCH("ls_scan_tiles_kernel");
+    if (int rc = set_smem(ls_scatter_tiles_kernel<false>, csm)) return rc;
+    ls_scatter_tiles_kernel<false><<<gc, kChunk, csm, s>>>(m, w.run_cnt, w.run_vox, w.hist, w.tile_ptr, w.bucket);
+  }
   SGV3D_CHECK_LAUNCH("ls_scatter_tiles_kernel");
   // heavy tiles (dense feature maps) get more warps: the kernel's tail is its most populated tile
   if ((long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1) > 1024)
@@ -1766,15 +1880,11 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   const int gpad = m.Cpad;  // gradient rows share the context rows' (permuted) channel layout
-  if (m.G == 4) {
-    // fused path: grad_bev -> one row per voxel, then everything else per pixel chunk in one kernel
-    const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
-    if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
-    ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
-    SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
-    return desc->ctx_dtype == SGV3D_DTYPE_BF16
-               ? launch_backward_chunk<__nv_bfloat16>(m, w, height, context, grad_height, grad_context, s)
-               : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s);
+  if (m.C <= 96) {
+    // fused path: 4-lane gradient rows of its own (16 * ceil(C / 16) floats <= Cpad, so gT is large enough)
+    Dims mb = m;
+    mb.G = 4; mb.NV = ceil_div(m.C, 16); mb.Cpad = 16 * mb.NV;
+    return launch_backward_fused(mb, w, desc->ctx_dtype, grad_bev, height, context, grad_height, grad_context, s);
   }
   if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, false, s)) return rc;
   launch_transpose_pad<float, float, 1>(grad_bev, w.gT, m.B, m.C, m.V, m.V, (size_t)m.C * m.V, gpad,
