@@ -474,7 +474,7 @@ ls_scan_tiles_kernel(Dims m, int *__restrict__ hist, int *__restrict__ tile_ptr)
 // ---------------------------------------------------------------------------------------------
 // The chunk's run keys (voxel ids), staged in shared memory: keys[r][t] for r < kScatRows; runs beyond
 // that (very long rays) are read from the ELL table directly.
-constexpr int kScatRows = 64;
+constexpr int kScatRows = 32;
 struct EllInput {
   const int *keys_s;   // shared: [kScatRows][kChunk]
   const int *run_vox;  // global ELL table
@@ -630,14 +630,26 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
   const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1);
   const int lo = tp[tile], hi = tp[tile + 1];
   if (hi == lo) return;
-  for (int i = t; i < kFinWarps * 64; i += kFinWarps * 32) (&s_cnt[0][0])[i] = 0;
-  __syncthreads();
   const int n = hi - lo;
   const int per = (n + kFinWarps - 1) / kFinWarps;
   const int wb = lo + min(wid * per, n), we = lo + min((wid + 1) * per, n);
   const BucketEnt *bk = bucket + (size_t)b * m.cap;
   int *my = s_cnt[wid];
-  for (int i = wb + lane; i < we; i += 32) atomicAdd(&my[bk[i].key & 63u], 1);
+  // the warp's first kFinRegs * 32 entries stay in registers for both passes (all loads in flight at once)
+  constexpr int kFinRegs = kFinWarps >= 16 ? 4 : 8;
+  uint2 er[kFinRegs];
+#pragma unroll
+  for (int k = 0; k < kFinRegs; ++k) {
+    const int i = wb + k * 32 + lane;
+    er[k] = make_uint2(0u, 0u);
+    if (i < we) er[k] = __ldg(reinterpret_cast<const uint2 *>(bk + i));
+  }
+  for (int i = t; i < kFinWarps * 64; i += kFinWarps * 32) (&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kFinRegs; ++k)
+    if (wb + k * 32 + lane < we) atomicAdd(&my[er[k].x & 63u], 1);
+  for (int i = wb + kFinRegs * 32 + lane; i < we; i += 32) atomicAdd(&my[bk[i].key & 63u], 1);
   __syncthreads();
   if (wid == 0) {  // 64 voxels, two per lane: totals -> exclusive scan -> per-warp bases
     int c[2][kFinWarps], tot[2];
@@ -671,14 +683,9 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
   const unsigned lt = lanemask_lt();
   Entry *ve = vm_ent + (size_t)b * m.cap;
   int *rd = run_dst + (size_t)b * m.cap;
-  for (int i0 = wb; i0 < we; i0 += 32) {
-    const int i = i0 + lane;
-    const bool valid = i < we;
-    BucketEnt e;
-    e.key = 0; e.slot = 0;
-    if (valid) e = bk[i];
+  auto place = [&](bool valid, unsigned key, int slot) {
     // invalid lanes get a private pseudo-digit so that they never match a real one
-    const int dig = valid ? (int)(e.key & 63u) : 64 + lane;
+    const int dig = valid ? (int)(key & 63u) : 64 + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, dig);
     const int leader = __ffs(peers) - 1;
     const int rank = __popc(peers & lt);
@@ -689,10 +696,23 @@ ls_finish_tiles_kernel(Dims m, const int *__restrict__ tile_ptr, const BucketEnt
     }
     base = __shfl_sync(0xffffffffu, base, leader);
     if (valid) {
-      ve[base + rank].off = e.key;
-      rd[e.slot] = base + rank;
+      ve[base + rank].off = key;
+      rd[slot] = base + rank;
     }
     __syncwarp();
+  };
+#pragma unroll
+  for (int k = 0; k < kFinRegs; ++k) {
+    if (wb + k * 32 >= we) break;  // warp-uniform
+    place(wb + k * 32 + lane < we, er[k].x, (int)er[k].y);
+  }
+  for (int i0 = wb + kFinRegs * 32; i0 < we; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < we;
+    BucketEnt e;
+    e.key = 0; e.slot = 0;
+    if (valid) e = bk[i];
+    place(valid, e.key, e.slot);
   }
 }
 
@@ -719,6 +739,19 @@ __device__ __forceinline__ void stage_columns(float *col, const float *__restric
   __syncthreads();
 }
 
+// exp(x) through the hardware 2^t unit (MUFU.EX2) with a compensated argument: t = x * log2(e) is formed as
+// t_hi + t_lo (t_hi the rounded leading product, t_lo its exact residual plus the low part of log2(e)), and
+// 2^(t_hi + t_lo) = 2^t_hi * (1 + t_lo ln 2) to first order (|t_lo| < 2^-20 for |x| < 100).  Error ~2 ulp
+// (ex2.approx's own 2^-22.5 bound), i.e. libm expf's accuracy class at a third of its instructions.
+__device__ __forceinline__ float exp_ex2(float x) {
+  const float kHi = 1.44269502162933349609375f, kLo = 1.925963033500011e-8f, kLn2 = 0.693147182464599609375f;
+  const float t_hi = __fmul_rn(x, kHi);
+  const float t_lo = __fmaf_rn(x, kLo, __fmaf_rn(x, kHi, -t_hi));
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t_hi));
+  return x < -104.0f ? 0.0f : __fmaf_rn(r, __fmul_rn(t_lo, kLn2), r);  // exp(-inf) = 0; NaN propagates
+}
+
 // Softmax over D of this thread's staged column (torch.softmax within fp32 rounding:
 // exp(x - max) / sum).  Leaves the un-normalised exponentials in col and returns 1 / sum, so the
 // normalisation costs one multiply per run / per output instead of a pass over the column.
@@ -737,7 +770,7 @@ __device__ __forceinline__ float softmax_column(float *col, int D, int t) {
   for (; d + 4 <= D; d += 4) {
     float e[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) e[k] = expf(__fsub_rn(col[(d + k) * kChunk + t], m));
+    for (int k = 0; k < 4; ++k) e[k] = exp_ex2(__fsub_rn(col[(d + k) * kChunk + t], m));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       col[(d + k) * kChunk + t] = e[k];
@@ -745,7 +778,7 @@ __device__ __forceinline__ float softmax_column(float *col, int D, int t) {
     }
   }
   for (; d < D; ++d) {
-    const float e = expf(__fsub_rn(col[d * kChunk + t], m));
+    const float e = exp_ex2(__fsub_rn(col[d * kChunk + t], m));
     col[d * kChunk + t] = e;
     s[0] = __fadd_rn(s[0], e);
   }
@@ -777,7 +810,7 @@ __device__ __forceinline__ float column_exp_sum(float *col, int lo, int hi, int 
   for (; d + 4 <= hi; d += 4) {
     float e[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) e[k] = expf(__fsub_rn(col[(d + k) * kChunk + t], m));
+    for (int k = 0; k < 4; ++k) e[k] = exp_ex2(__fsub_rn(col[(d + k) * kChunk + t], m));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       col[(d + k) * kChunk + t] = e[k];
@@ -785,7 +818,7 @@ __device__ __forceinline__ float column_exp_sum(float *col, int lo, int hi, int 
     }
   }
   for (; d < hi; ++d) {
-    const float e = expf(__fsub_rn(col[d * kChunk + t], m));
+    const float e = exp_ex2(__fsub_rn(col[d * kChunk + t], m));
     col[d * kChunk + t] = e;
     s[0] = __fadd_rn(s[0], e);
   }
@@ -1428,7 +1461,7 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__r
     float sm = 0.0f;
     if (live)
       for (int d = l; d < m.D; d += 4) {
-        const float e = expf(__fsub_rn(col[d * kBwdPix + px], mx));
+        const float e = exp_ex2(__fsub_rn(col[d * kBwdPix + px], mx));
         col[d * kBwdPix + px] = e;
         sm = __fadd_rn(sm, e);
       }
