@@ -183,6 +183,22 @@ class LiftSplatPlan:
         self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=g.device)
         self.rebuild()
 
+    def update_calibration(self, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
+                           bda_mat) -> None:
+        """New matrices for the same batch shape: the derived per-camera operands are overwritten in place
+        and the plan is rebuilt into the same workspace."""
+        g = self.geometry
+        ida_inv, m_virtual, m_ego = camera_matrices(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat)
+        g.ida_inv.copy_(ida_inv.reshape(g.ida_inv.shape))
+        g.m_virtual.copy_(m_virtual.reshape(g.m_virtual.shape))
+        g.m_ego.copy_(m_ego.reshape(g.m_ego.shape))
+        g.ref_h.copy_(reference_heights.reshape(-1))
+        if (g.bda is None) != (bda_mat is None):
+            raise RuntimeError("update_calibration cannot add or remove the BDA matrix")
+        if bda_mat is not None:
+            g.bda.copy_(bda_mat)
+        self.rebuild()
+
     def rebuild(self) -> None:
         g = self.geometry
         with torch.cuda.device(self.device):
@@ -401,10 +417,11 @@ class LiftSplat(nn.Module):
         """LSSFPN: ``height_feature`` = (B*Nc, D + C, fH, fW) output of the height net
         (lss_fpn.py:461).  Returns the (B, C, Y, X) contiguous BEV map of lss_fpn.py:494-495."""
         d, c = self.height_channels, self.output_channels
+        hf = height_feature.float()
         plan = self.make_plan(mats_dict, sweep_index, c)
         # softmax over the D logits (lss_fpn.py:462), lift (:464-466), geometry (:478-488) and pooling
         # (:490-495) all happen inside the library, on the head's output tensor in place
-        return _LiftSplatHeadFunction.apply(height_feature.float(), plan, d, c)
+        return _LiftSplatHeadFunction.apply(hf, plan, d, c)
 
     def forward_single_sweep_bsm(self, height_logits, semantic_logits, context, mats_dict,
                                  sweep_index: int = 0) -> torch.Tensor:
@@ -433,27 +450,52 @@ class LiftSplatGraph:
     """
 
     def __init__(self, module: LiftSplat, height_feature: torch.Tensor, mats_dict, sweep_index: int = 0,
-                 warmup: int = 2):
+                 warmup: int = 2, static_calibration: bool = False):
         if not height_feature.is_cuda:
             raise RuntimeError("sgv3d_b200 runs on CUDA tensors only (no CPU fallback)")
         self.module, self.sweep_index = module, sweep_index
         self.height_feature = height_feature
         self.mats_dict = mats_dict
         self.device = height_feature.device
+        self.static_calibration = static_calibration
+        d, c = module.height_channels, module.output_channels
+        # static roadside camera (IDA deterministic, BDA identity at inference: dataset/nusc_mv_det_dataset.py:433-454):
+        # the voxel-run plan is built once, outside the graph; a replay is the two forward kernels only
+        self.plan = module.make_plan(mats_dict, sweep_index, c) if static_calibration else None
+
+        def step():
+            if self.plan is not None:
+                hf = height_feature.float()
+                return self.plan.forward(hf[:, :d], hf[:, d:d + c], logits=True)
+            return module.forward_single_sweep(height_feature, mats_dict, sweep_index)
+
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(max(1, warmup)):   # lazy initialisation (cuBLAS handles, smem attributes) before capture
-                module.forward_single_sweep(height_feature, mats_dict, sweep_index)
+                step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
-            self.bev = module.forward_single_sweep(height_feature, mats_dict, sweep_index)
+            self.bev = step()
+
+    def refresh_calibration(self, mats_dict=None) -> None:
+        """``static_calibration`` mode: rebuild the plan in place (same workspace, so the captured graph
+        stays valid) after the camera was re-calibrated."""
+        if self.plan is None:
+            raise RuntimeError("refresh_calibration() is for static_calibration=True graphs")
+        m = mats_dict if mats_dict is not None else self.mats_dict
+        i = self.sweep_index
+        self.plan.update_calibration(m["sensor2ego_mats"][:, i, ...], m["sensor2virtual_mats"][:, i, ...],
+                                     m["intrin_mats"][:, i, ...], m["ida_mats"][:, i, ...],
+                                     m["reference_heights"][:, i, ...], m.get("bda_mat", None))
 
     def __call__(self, height_feature: Optional[torch.Tensor] = None, mats_dict=None) -> torch.Tensor:
         if height_feature is not None and height_feature is not self.height_feature:
             self.height_feature.copy_(height_feature, non_blocking=True)
         if mats_dict is not None and mats_dict is not self.mats_dict:
+            if self.static_calibration:
+                raise RuntimeError("static_calibration graph: call refresh_calibration(mats_dict) to change the matrices")
             for k, v in mats_dict.items():
                 if v is not None and self.mats_dict.get(k) is not None:
                     self.mats_dict[k].copy_(v, non_blocking=True)

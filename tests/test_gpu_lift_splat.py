@@ -244,3 +244,69 @@ def test_stacked_inverse_is_bit_identical(batch):
         want = (ida.inverse(), s2v.matmul(torch.inverse(k)), s2e.matmul(torch.inverse(s2v)))
         for g, w in zip(got, want):
             assert torch.equal(g.contiguous().view(torch.int32), w.contiguous().view(torch.int32))
+
+
+@pytest.mark.parametrize("channels", [3, 32, 33, 64, 96, 97, 128, 160, 200, 256])
+def test_channel_sweep_covers_every_row_layout(channels):
+    """BASELINE config 5 sweeps 64-256 channels: every (lanes per row, vectors per lane) instantiation of the
+    reduce / backward kernels against the fp64 oracle, with the softmax fused (logits in)."""
+    from sgv3d_b200.view_transform import LiftSplatPlan
+    shape = get_shape("small")
+    B = 2
+    mats = make_mats(shape, B, 1, seed=40 + channels, bda="identity")
+    fr = oracle_frustum(shape)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    dev = {k: v.cuda() for k, v in mats.items()}
+    plan = LiftSplatPlan(fr, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"],
+                         dev["reference_heights"], dev["bda"], vc, vs, shape.grid, channels, arith=0)
+    ida_inv, mv, me = O.camera_matrices(dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"])
+    u, v, z = (t.numpy() for t in frustum_axes(fr))
+    xyz = CO.geometry(0, u, v, z, ida_inv.cpu().numpy(), mv.cpu().numpy(), me.cpu().numpy(),
+                      mats["reference_heights"].numpy(), mats["bda"].numpy())
+    idx = CO.quantize(xyz, (vc - vs / 2.0).numpy(), vs.numpy())
+    logits, ctx = make_activations(shape, B, 1, seed=channels, channels=channels)
+    X, Y, Z = shape.grid
+    bev = plan.forward(logits.cuda(), ctx.cuda(), logits=True)
+    height = logits.softmax(1)
+    want = CO.lift_splat_forward64(idx, height.numpy(), ctx.numpy(), X, Y, Z)
+    np.testing.assert_allclose(bev.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(channels))
+    g_h, g_c = plan.backward(gb.cuda(), height.cuda(), ctx.cuda())
+    gh64, gc64 = CO.lift_splat_backward64(idx, height.numpy(), ctx.numpy(), gb.numpy(), X, Y, Z)
+    np.testing.assert_allclose(g_h.cpu().numpy(), gh64, rtol=RTOL, atol=ATOL * 10)
+    np.testing.assert_allclose(g_c.cpu().numpy(), gc64, rtol=RTOL, atol=ATOL)
+
+
+def test_static_calibration_graph_and_refresh():
+    """LiftSplatGraph(static_calibration=True): plan built once outside the graph (static roadside camera),
+    replays bit-identical to the per-step path; refresh_calibration() swaps the matrices in place."""
+    from sgv3d_b200 import LiftSplat, LiftSplatGraph
+    shape = get_shape("small")
+    B = 2
+
+    def md_of(seed):
+        mats = make_mats(shape, B, 1, seed=seed, bda="identity")
+        return {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).cuda(),
+                "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).cuda(),
+                "intrin_mats": mats["intrin"].unsqueeze(1).cuda(), "ida_mats": mats["ida"].unsqueeze(1).cuda(),
+                "reference_heights": mats["reference_heights"].unsqueeze(1).cuda(), "bda_mat": mats["bda"].cuda()}
+
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                    shape.downsample, shape.channels).cuda()
+    md_a, md_b = md_of(71), md_of(72)
+    logits, ctx = make_activations(shape, B, 1, seed=7)
+    hf = torch.cat((logits, ctx), 1).cuda()
+    with torch.no_grad():
+        want_a = mod.forward_single_sweep(hf, md_a).clone()
+        want_b = mod.forward_single_sweep(hf, md_b).clone()
+    assert not torch.equal(want_a, want_b)
+    g = LiftSplatGraph(mod, hf.clone(), md_a, static_calibration=True)   # the graph owns its input buffer
+    assert torch.equal(g(), want_a)
+    hf2 = hf * 0.5 + 0.1
+    with torch.no_grad():
+        want_a2 = mod.forward_single_sweep(hf2, md_a).clone()
+    assert torch.equal(g(hf2), want_a2)      # new activations are copied into the captured input
+    g.refresh_calibration(md_b)
+    assert torch.equal(g(hf), want_b)
+    with pytest.raises(RuntimeError):
+        g(hf, md_b)     # a different mats_dict must go through refresh_calibration()
