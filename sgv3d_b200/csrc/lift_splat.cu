@@ -11,32 +11,29 @@
 //     ls_plan_runs_*_kernel   thread/pixel walks D: bit-exact geometry -> voxel id -> run-length
 //                             encoding, emitted pixel-major in an ELL layout; per-chunk histogram of the
 //                             runs over 64-voxel tiles
-//     ls_scan_tiles_kernel    per frame: exclusive scan of the histograms (over chunks, then over tiles)
-//     ls_scatter_tiles_kernel stable scatter of the runs into per-tile buckets (MSD pass: one digit = the tile)
-//     ls_finish_tiles_kernel  per tile: stable counting sort of its bucket by voxel-in-tile, CSR offsets per
-//                             voxel, inverse permutation (run -> sorted slot)
+//     ls_scatter_tiles_kernel stable scatter of the runs into per-tile buckets (MSD pass: one digit = the tile);
+//                             for small grids the scan of the histograms is done here, per CTA
+//                             (ls_scan_tiles_kernel otherwise)
+//     ls_finish_tiles_kernel  per tile: stable counting sort of its bucket by voxel-in-tile, sorted entries,
+//                             inverse permutation (run -> sorted slot)
 //     Ties keep the canonical (chunk, warp, run index, lane) order => the per-voxel summation order is a
 //     pure function of the calibration: deterministic, no floating-point atomics.
 //   FORWARD (values)
-//     transpose_pad_kernel    context NCHW -> one 16B-aligned row per pixel
-//     ls_weights_kernel       [softmax over D fused] w[run] = sum_{d in run} p[d,pixel]; the height
-//                             columns of 128 pixels are staged in smem with cp.async (all loads in flight)
-//     ls_reduce_kernel        one warp per 8-voxel strip (no block barriers): per voxel
-//                             sum_j w[j] * ctx_row[pixel_j] in sorted (deterministic) order, 8 row
-//                             loads in flight, written as 32-byte sectors of the NCHW output
+//     ls_lift_prep_kernel     two kinds of CTA in one launch: [softmax over D fused] w[run] = sum_{d in run}
+//                             p[d,pixel] from cp.async-staged height columns, written to the run's sorted entry;
+//                             context NCHW -> one channels-last row of whole 128-byte lines per pixel
+//     ls_reduce_kernel        CTA = 64-voxel tile, entry list cut into equal slices per 8-lane stream, rows
+//                             gathered as full 128-byte lines, sums in a fixed order, NCHW tile written once
 //   BACKWARD (values; pixel-major, no sort needed)
-//     transpose_pad_kernel    grad_bev NCHW -> one row per voxel
-//     ls_weights_kernel       w per run (pixel-major destination)
-//     ls_backward_gather_kernel  warp/pixel: g_ctx_row = sum_r w_r*G[voxel_r]; gw_r = <ctx_row, G[voxel_r]>
-//     ls_expand_kernel        g_height[d,pixel] = gw[run(d)] (0 for dropped bins) [softmax backward fused]
-//     transpose_pad_kernel    g_ctx rows -> NCHW
+//     ls_grad_rows_kernel     grad_bev NCHW -> one row per voxel (touched tiles only)
+//     ls_backward_chunk_kernel per 64-pixel chunk: softmax, run weights, g_ctx_row = sum_r w_r*G[voxel_r],
+//                             gw_r = <ctx_row, G[voxel_r]>, softmax backward, g_height / g_ctx NCHW writes
+//     (C > 96: ls_lift_prep_kernel, transpose_pad_kernel, ls_backward_gather_kernel, ls_expand_kernel)
 //
 // No floating-point atomics anywhere; every sum has a fixed order => bitwise reproducible.
 #include <cuda_bf16.h>
-#include <stdlib.h>
 
 #include <algorithm>
-#include <stdlib.h>
 
 #include "geometry.cuh"
 #include "sort.cuh"
@@ -1696,11 +1693,8 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
   int stage_cap = 1536;
   while (stage_cap < 2 * expect && stage_cap < 6144) stage_cap += 1536;
-  if (const char *e = getenv("SGV3D_EXP_STAGE")) stage_cap = atoi(e);
   const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * stage_cap;
   if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR>, smem)) return rc;
-  if (const char *e = getenv("SGV3D_EXP_CARVE"))
-    SGV3D_CUDA(cudaFuncSetAttribute(ls_reduce_kernel<CT, G, NV, NSTR>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
   ls_reduce_kernel<CT, G, NV, NSTR><<<grid, NSTR * G, smem, s>>>(
@@ -1714,8 +1708,7 @@ int launch_reduce_nstr(const Dims &m, const Workspace &w, float *bev, cudaStream
   // streams per tile by the expected tile population (pixels * ~25 runs / ~2/3 of the tiles touched): a tile is
   // one CTA, so the most populated tiles of a dense feature map (stride 8) set the kernel's tail
   const long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
-  int nstr = expect > 6000 ? 128 : (expect > 1500 ? 64 : 32);
-  if (const char *e = getenv("SGV3D_EXP_NSTR")) nstr = atoi(e);
+  const int nstr = expect > 6000 ? 128 : (expect > 1500 ? 64 : 32);
   if (nstr == 128) return launch_reduce_cfg<CT, G, NV, 128>(m, w, bev, s);
   if (nstr == 64) return launch_reduce_cfg<CT, G, NV, 64>(m, w, bev, s);
   return launch_reduce_cfg<CT, G, NV, 32>(m, w, bev, s);
