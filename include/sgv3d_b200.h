@@ -157,6 +157,21 @@ SGV3D_API int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const 
                              const void *context, float *bev, void *workspace,
                              size_t workspace_bytes, sgv3d_stream_t stream);
 
+/* BSMLSSFPN call site (bsm_lss_fpn.py:523-559), inference: the context assembly of bsm_lss_fpn.py:524-529
+ *   semantic = softmax(semantic_logits, channel axis)
+ *   tran_feat = cat(context, semantic) * (1 - (semantic[:, 0] > background_threshold))
+ * happens inside the forward's context pass; the C = (C - Cs) + Cs channel tensor is never materialised.
+ *     context          fp32 [B*Nc, C - Cs, fH, fW]   (desc->ctx_batch_stride: elements between cameras, 0 = dense)
+ *     semantic_logits  fp32 [B*Nc, Cs, fH, fW]       (semantic_batch_stride likewise)
+ * desc->C is the BEV channel count (87 = 80 + 7 in exps/sgv3d/...:40,88); desc->ctx_dtype must be F32.
+ * The softmax restates torch's CUDA softmax over a channel axis (per pixel: max, sum of exp(x - max) in
+ * channel order, exp(x - max) / sum), so the background mask is bit-identical to the reference's. */
+SGV3D_API int sgv3d_lift_splat_forward_bsm(const sgv3d_lift_splat_desc *desc, const float *height,
+                                 const float *context, const float *semantic_logits,
+                                 int semantic_channels, int64_t semantic_batch_stride,
+                                 float background_threshold, float *bev, void *workspace,
+                                 size_t workspace_bytes, sgv3d_stream_t stream);
+
 /* grad_height fp32 [B*Nc, D, fH, fW], grad_context fp32 [B*Nc, C, fH, fW]; both fully written.
  * grad_bev fp32 [B, C, Y, X] contiguous. */
 SGV3D_API int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, const float *grad_bev,

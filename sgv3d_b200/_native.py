@@ -23,7 +23,7 @@ SYMBOLS = (
     "sgv3d_voxel_pooling_backward_workspace_bytes", "sgv3d_voxel_pooling_backward",
     "sgv3d_geometry_quantize",
     "sgv3d_lift_splat_workspace_bytes", "sgv3d_lift_splat_plan", "sgv3d_lift_splat_forward",
-    "sgv3d_lift_splat_backward", "sgv3d_lift_splat_plan_expand",
+    "sgv3d_lift_splat_forward_bsm", "sgv3d_lift_splat_backward", "sgv3d_lift_splat_plan_expand",
     "sgv3d_profile_enable", "sgv3d_profile_report",
 )
 
@@ -74,6 +74,9 @@ def lib() -> ctypes.CDLL:
     L.sgv3d_lift_splat_plan.argtypes = [P] + [c_void_p] * 11 + [c_size_t, c_void_p]
     L.sgv3d_lift_splat_forward.restype = c_int
     L.sgv3d_lift_splat_forward.argtypes = [P] + [c_void_p] * 4 + [c_size_t, c_void_p]
+    L.sgv3d_lift_splat_forward_bsm.restype = c_int
+    L.sgv3d_lift_splat_forward_bsm.argtypes = ([P] + [c_void_p] * 3 + [c_int, c_int64, ctypes.c_float]
+                                               + [c_void_p] * 2 + [c_size_t, c_void_p])
     L.sgv3d_lift_splat_backward.restype = c_int
     L.sgv3d_lift_splat_backward.argtypes = [P] + [c_void_p] * 6 + [c_size_t, c_void_p]
     L.sgv3d_lift_splat_plan_expand.restype = c_int

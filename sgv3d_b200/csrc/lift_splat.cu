@@ -894,31 +894,61 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
 // order, transpose.cuh: RowPerm).  Reads are coalesced 512-byte channel rows (cp.async, all in flight at
 // once), writes are coalesced 128-byte pieces of the pixel rows; the smem tile is [C][129] (conflict-free
 // both ways: consecutive pixels on the way in, 32 distinct channels of one pixel on the way out).
+// BSMLSSFPN context assembly (bsm_lss_fpn.py:524-529), fused into the context-rows pass when `sem` is set:
+//   semantic = softmax(sem, channel axis);  rows = cat(context, semantic) * (1 - (semantic[0] > thr))
+// The last Cs of the C row channels are the semantic probabilities; `context` holds the other C - Cs.
+struct BsmAssembly {
+  const float *sem;      // [B*Nc, Cs, fH, fW] semantic logits, or nullptr
+  long long sem_stride;  // elements between consecutive cameras
+  int Cs;
+  float thr;
+};
+
 template <typename CT>
 __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__restrict__ context,
                                                   CT *__restrict__ ctxT, RowPerm perm, float *smem, int b,
-                                                  int chunk) {
+                                                  int chunk, const BsmAssembly &bsm) {
   constexpr int kLd = kChunk + 1;
   constexpr int kWarps = kPrepThreads / 32, kQ = kPrepThreads / kChunk;
+  __shared__ float s_keep[kChunk];  // BSM: 0 for background pixels, else 1
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int t = threadIdx.x & (kChunk - 1), q = threadIdx.x / kChunk;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int p0 = ci * kChunk;
   const int npx = min(kChunk, m.P - p0);
+  const int Cc = m.C - (bsm.sem ? bsm.Cs : 0);  // channels that come from `context`
   const CT *src = context + (size_t)(b * m.Nc + n) * m.cs + p0 + t + (size_t)q * m.P;
   if (t < npx) {
     float *sp = smem + q * kLd + t;
     if (sizeof(CT) == 4) {
 #pragma unroll 4
-      for (int c = q; c < m.C; c += kQ, sp += kQ * kLd, src += (size_t)kQ * m.P)
+      for (int c = q; c < Cc; c += kQ, sp += kQ * kLd, src += (size_t)kQ * m.P)
         cp_async_4(sp, reinterpret_cast<const float *>(src));
+      if (bsm.sem) {
+        const float *ss = bsm.sem + (size_t)(b * m.Nc + n) * bsm.sem_stride + p0 + t;
+        for (int k = q; k < bsm.Cs; k += kQ) cp_async_4(smem + (Cc + k) * kLd + t, ss + (size_t)k * m.P);
+      }
     } else {
 #pragma unroll 4
-      for (int c = q; c < m.C; c += kQ, sp += kQ * kLd, src += (size_t)kQ * m.P) *sp = to_f32<CT>(*src);
+      for (int c = q; c < Cc; c += kQ, sp += kQ * kLd, src += (size_t)kQ * m.P) *sp = to_f32<CT>(*src);
     }
   }
   cp_async_wait_all();
   __syncthreads();
+  if (bsm.sem) {  // block-uniform
+    if (q == 0 && t < npx) {
+      // torch.softmax over the channel axis of an NCHW tensor (spatial softmax kernel: one thread per pixel,
+      // sequential over the channels): max, sum += exp(x - max) in channel order, exp(x - max) / sum
+      float *col = smem + Cc * kLd + t;
+      float mx = col[0];
+      for (int k = 1; k < bsm.Cs; ++k) mx = fmaxf(mx, col[k * kLd]);
+      float sum = 0.0f;
+      for (int k = 0; k < bsm.Cs; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(col[k * kLd], mx)));
+      for (int k = 0; k < bsm.Cs; ++k) col[k * kLd] = __fdiv_rn(expf(__fsub_rn(col[k * kLd], mx)), sum);
+      s_keep[t] = col[0] > bsm.thr ? 0.0f : 1.0f;  // (1 - mask.int()) of bsm_lss_fpn.py:528-529
+    }
+    __syncthreads();
+  }
   CT *dst = ctxT + ((size_t)(b * m.Nc + n) * m.P + p0) * m.Cpad;
   // lane <-> element of the row (3 pieces of 32 elements cover Cpad <= 96; loop for wider rows); everything
   // that depends on the element only is hoisted out of the pixel loop
@@ -930,8 +960,13 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
     const size_t dstep = (size_t)kWarps * m.Cpad;
     if (c < m.C) {
       const float *sp = smem + c * kLd + wid;
+      if (bsm.sem) {
+        for (int px = wid; px < npx; px += kWarps, sp += kWarps, dp += dstep)
+          *dp = from_f32<CT>(__fmul_rn(*sp, s_keep[px]));
+      } else {
 #pragma unroll 4
-      for (int px = wid; px < npx; px += kWarps, sp += kWarps, dp += dstep) *dp = from_f32<CT>(*sp);
+        for (int px = wid; px < npx; px += kWarps, sp += kWarps, dp += dstep) *dp = from_f32<CT>(*sp);
+      }
     } else {
       for (int px = wid; px < npx; px += kWarps, dp += dstep) *dp = from_f32<CT>(0.0f);
     }
@@ -945,11 +980,11 @@ __global__ void __launch_bounds__(kPrepThreads)
 ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
                     const int *__restrict__ run_d, const int *__restrict__ run_dst,
                     float *__restrict__ w_pm_out, Entry *__restrict__ vm_ent_out,
-                    const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm) {
+                    const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm, BsmAssembly bsm) {
   extern __shared__ float lift_smem[];
   if (blockIdx.z == 0)
     weights_role(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x);
-  else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x);
+  else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x, bsm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1770,7 +1805,7 @@ int launch_backward_gather(const Dims &m, const Workspace &w, int gpad, cudaStre
 
 // weights + context rows in one launch (forward and backward need both)
 int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const float *height, const void *context,
-                     bool forward, cudaStream_t s) {
+                     bool forward, cudaStream_t s, BsmAssembly bsm = BsmAssembly{nullptr, 0, 0, 0.0f}) {
   Entry *vm_out = forward ? w.vm_ent : nullptr;
   dim3 grid(m.nchunks, m.B, 2);
   const size_t smem = sizeof(float) * (size_t)(m.D > m.C ? m.D * kChunk : m.C * (kChunk + 1));
@@ -1780,12 +1815,12 @@ int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const flo
     if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16>, smem2)) return rc;
     ls_lift_prep_kernel<__nv_bfloat16><<<grid, kPrepThreads, smem2, s>>>(
         m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm, vm_out, static_cast<const __nv_bfloat16 *>(context),
-        static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m));
+        static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m), bsm);
   } else {
     if (int rc = set_smem(ls_lift_prep_kernel<float>, smem2)) return rc;
     ls_lift_prep_kernel<float><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
                                                           vm_out, static_cast<const float *>(context),
-                                                          static_cast<float *>(w.ctxT), row_perm(m));
+                                                          static_cast<float *>(w.ctxT), row_perm(m), bsm);
   }
   SGV3D_CHECK_LAUNCH("ls_lift_prep_kernel");
   return SGV3D_OK;
@@ -1889,6 +1924,34 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   prof_begin(s);
   if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, true, s)) return rc;
   if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
+  return launch_reduce<float>(m, w, bev, s);
+}
+
+extern "C" int sgv3d_lift_splat_forward_bsm(const sgv3d_lift_splat_desc *desc, const float *height,
+                                            const float *context, const float *semantic_logits,
+                                            int semantic_channels, int64_t semantic_batch_stride,
+                                            float background_threshold, float *bev, void *workspace,
+                                            size_t workspace_bytes, sgv3d_stream_t stream) {
+  if (int rc = validate(desc, "lift_splat_forward_bsm")) return rc;
+  if (desc->B == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(height && context && semantic_logits && bev, "lift_splat_forward_bsm: null pointer");
+  SGV3D_REQUIRE(desc->ctx_dtype == SGV3D_DTYPE_F32, "lift_splat_forward_bsm: fp32 context only");
+  SGV3D_REQUIRE(semantic_channels > 0 && semantic_channels < desc->C,
+                "lift_splat_forward_bsm: semantic_channels must be in (0, C)");
+  SGV3D_REQUIRE(semantic_batch_stride >= 0, "lift_splat_forward_bsm: negative batch stride");
+  Dims m = make_dims(desc);
+  // `context` holds the C - Cs feature channels: its dense camera block is that much smaller
+  if (!desc->ctx_batch_stride) m.cs = (long long)(m.C - semantic_channels) * m.P;
+  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward_bsm")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
+  BsmAssembly bsm;
+  bsm.sem = semantic_logits;
+  bsm.sem_stride = semantic_batch_stride ? semantic_batch_stride : (long long)semantic_channels * m.P;
+  bsm.Cs = semantic_channels;
+  bsm.thr = background_threshold;
+  if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, true, s, bsm)) return rc;
   return launch_reduce<float>(m, w, bev, s);
 }
 

@@ -227,6 +227,33 @@ class LiftSplatPlan:
                                                      self.ws_bytes, N.current_stream()))
         return bev
 
+    def forward_bsm(self, height: torch.Tensor, context: torch.Tensor, semantic_logits: torch.Tensor,
+                    threshold: float = 0.45, logits: bool = True) -> torch.Tensor:
+        """BSMLSSFPN forward with the context assembly of bsm_lss_fpn.py:524-529 fused (inference, no autograd):
+        ``context`` (BN, C - Cs, fH, fW) and ``semantic_logits`` (BN, Cs, fH, fW) are consumed in place; the
+        masked (BN, C, fH, fW) tensor is never built."""
+        d = self.desc
+        bn, cs = d.B * d.Nc, int(semantic_logits.shape[1])
+        cc = d.C - cs
+        if self.ctx_dtype != torch.float32:
+            raise RuntimeError("forward_bsm: float32 context only")
+        for name, t, ch in (("height", height, d.D), ("context", context, cc), ("semantic_logits", semantic_logits, cs)):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise RuntimeError(f"forward_bsm: {name} must be a float32 CUDA tensor")
+            assert tuple(t.shape) == (bn, ch, d.fH, d.fW), (name, tuple(t.shape), (bn, ch, d.fH, d.fW))
+        height, context, semantic_logits = _dense_blocks(height), _dense_blocks(context), _dense_blocks(semantic_logits)
+        c = N.LiftSplatDesc.from_buffer_copy(d)
+        c.height_is_logits = 1 if logits else 0
+        c.height_batch_stride = _camera_block_stride(height, d.D, d.fH, d.fW, "height")
+        c.ctx_batch_stride = _camera_block_stride(context, cc, d.fH, d.fW, "context")
+        sem_stride = _camera_block_stride(semantic_logits, cs, d.fH, d.fW, "semantic_logits")
+        bev = torch.empty(d.B, d.C, d.Y, d.X, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sgv3d_lift_splat_forward_bsm(c, N.ptr(height), N.ptr(context), N.ptr(semantic_logits), cs,
+                                                         sem_stride, float(threshold), N.ptr(bev), N.ptr(self.ws),
+                                                         self.ws_bytes, N.current_stream()))
+        return bev
+
     def backward(self, grad_bev: torch.Tensor, height: torch.Tensor, context: torch.Tensor, logits: bool = False,
                  out_height: Optional[torch.Tensor] = None, out_context: Optional[torch.Tensor] = None):
         """Gradients w.r.t. ``height`` (w.r.t. the logits when ``logits=True``) and ``context``; optionally
@@ -428,6 +455,12 @@ class LiftSplat(nn.Module):
         """BSMLSSFPN: ``out[0], out[1], out[2]`` of the MSCT head (bsm_lss_fpn.py:522-529): height
         logits (BN, D, fH, fW), 7 semantic logits, 80 context channels.  The 87-channel masked context
         is assembled exactly as the reference does, then lifted and splatted."""
+        if not (torch.is_grad_enabled() and (height_logits.requires_grad or semantic_logits.requires_grad
+                                             or context.requires_grad)):
+            # inference: softmax over the 7 semantic channels, concat and background mask (bsm_lss_fpn.py:524-529)
+            # run inside the forward's context pass; the 87-channel tensor is never built
+            plan = self.make_plan(mats_dict, sweep_index, int(context.shape[1] + semantic_logits.shape[1]))
+            return plan.forward_bsm(height_logits.float(), context.float(), semantic_logits.float(), 0.45)
         semantic = semantic_logits.softmax(dim=1)                               # bsm_lss_fpn.py:524
         tran_feat = torch.cat((context, semantic), dim=1)                       # :526
         mask = semantic[:, 0, :, :].unsqueeze(1) > 0.45                         # :528 background

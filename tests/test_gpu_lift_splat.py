@@ -310,3 +310,45 @@ def test_static_calibration_graph_and_refresh():
     assert torch.equal(g(hf), want_b)
     with pytest.raises(RuntimeError):
         g(hf, md_b)     # a different mats_dict must go through refresh_calibration()
+
+
+@pytest.mark.parametrize("shape_name,batch", [("small", 2), ("sgv3d_bsm_r50", 1)])
+def test_fused_bsm_assembly_is_bit_identical_to_the_torch_assembly(shape_name, batch):
+    """sgv3d_lift_splat_forward_bsm (softmax over the semantic channels + concat + background mask inside the
+    context pass, bsm_lss_fpn.py:524-529) == the same torch calls the reference makes, run on the GPU, followed by
+    the plain forward: the background mask must be bit-identical, hence the BEV map bitwise equal."""
+    from sgv3d_b200 import LiftSplat
+    shape = get_shape(shape_name)
+    bsm_native = shape_name == "sgv3d_bsm_r50"
+    fh, fw = (shape.fH, shape.fW) if bsm_native else (shape.fH * 2, shape.fW * 2)
+    mats = make_mats(shape, batch, 1, seed=43, bda="identity")
+    g = torch.Generator().manual_seed(11)
+    height_logits = torch.randn(batch, shape.D, fh, fw, generator=g).cuda()
+    # logits scaled so that the background probability straddles the 0.45 threshold for many pixels
+    semantic_logits = (torch.randn(batch, 7, fh, fw, generator=g) * 1.5).cuda()
+    semantic_logits[:, 0] += 1.6
+    context = torch.randn(batch, 80, fh, fw, generator=g).cuda()
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                    shape.downsample * (1 if bsm_native else 1), 87, is_bsm=not bsm_native).cuda()
+    if bsm_native:   # the named shape already carries the stride-8 map: build the module at that stride
+        mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                        shape.downsample, 87).cuda()
+    md = {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).cuda(), "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).cuda(),
+          "intrin_mats": mats["intrin"].unsqueeze(1).cuda(), "ida_mats": mats["ida"].unsqueeze(1).cuda(),
+          "reference_heights": mats["reference_heights"].unsqueeze(1).cuda(), "bda_mat": mats["bda"].cuda()}
+    with torch.no_grad():
+        fused = mod.forward_single_sweep_bsm(height_logits, semantic_logits, context, md)
+    # the reference's own calls (bsm_lss_fpn.py:524-529) on the GPU
+    semantic = semantic_logits.softmax(dim=1)
+    tran_feat = torch.cat((context, semantic), dim=1)
+    mask = semantic[:, 0, :, :].unsqueeze(1) > 0.45
+    frac = float(mask.float().mean())
+    assert 0.2 < frac < 0.8, frac          # the threshold is exercised on both sides
+    tran_feat = tran_feat * (1 - mask.int())
+    plan = mod.make_plan(md, 0, 87)
+    want = plan.forward(height_logits, tran_feat.float(), logits=True)
+    assert torch.equal(fused, want)
+    # and the autograd path (torch assembly) still gives the same values
+    hl = height_logits.clone().requires_grad_(True)
+    via_autograd = mod.forward_single_sweep_bsm(hl, semantic_logits, context, md)
+    assert torch.equal(via_autograd.detach(), want)
