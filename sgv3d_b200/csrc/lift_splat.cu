@@ -1743,8 +1743,8 @@ int launch_reduce_nstr(const Dims &m, const Workspace &w, float *bev, cudaStream
   // streams per tile by the expected tile population (pixels * ~25 runs / ~2/3 of the tiles touched): a tile is
   // one CTA, so the most populated tiles of a dense feature map (stride 8) set the kernel's tail
   const long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
-  // (small batches of a dense map are bound by the tail: twice the streams again; measured on BSM-R50)
-  const int nstr = expect > 6000 ? 128 : (expect > 1500 ? (m.B <= 8 ? 128 : 64) : 32);
+  // (small batches are bound by the tail: twice the streams again; measured on DAIR-R50 and BSM-R50)
+  const int nstr = expect > 6000 ? 128 : (expect > 1500 ? (m.B <= 8 ? 128 : 64) : (m.B <= 2 ? 64 : 32));
   if (nstr == 128) return launch_reduce_cfg<CT, G, NV, 128>(m, w, bev, s);
   if (nstr == 64) return launch_reduce_cfg<CT, G, NV, 64>(m, w, bev, s);
   return launch_reduce_cfg<CT, G, NV, 32>(m, w, bev, s);
