@@ -118,6 +118,14 @@ SGV3D_API int sgv3d_geometry_quantize(int arith, int B, int Nc, int D, int fH, i
                             const float *ref_heights, const float *lower3, const float *size3,
                             int32_t *idx_out, float *xyz_out, sgv3d_stream_t stream);
 
+/* Batched 4x4 inverse, bit-identical to torch.inverse on a CUDA fp32 tensor (what the reference calls at
+ * lss_fpn.py:361,367,392; cuBLAS batched LU + solves: reciprocal-scaled LU with partial pivoting and FMA
+ * updates, FMA forward / backward substitution, one division by the diagonal).  Up to three sets of n
+ * row-major matrices in one launch (ida, intrin, sensor2virtual); a1/inv1 and a2/inv2 may be NULL.
+ * Singular or non-finite matrices give unspecified non-finite output (as torch.linalg.inv_ex does). */
+SGV3D_API int sgv3d_inverse4x4(int n, const float *a0, const float *a1, const float *a2, float *inv0,
+                     float *inv1, float *inv2, sgv3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) fused lift-splat.  The plan (index) depends only on calibration + grid; forward/backward
  *     (values) depend on the activations.  Static roadside cameras can build the plan once.

@@ -22,7 +22,7 @@ from torch.autograd import Function
 
 from . import _native as N
 
-__all__ = ["camera_matrices", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat", "LiftSplatGraph",
+__all__ = ["camera_matrices", "inverse4x4", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat", "LiftSplatGraph",
            "build_frustum", "default_arith"]
 
 _DEFAULT_ARITH = N.ARITH_PAIR
@@ -62,10 +62,61 @@ def _inverse(x: torch.Tensor) -> torch.Tensor:
     return torch.linalg.inv_ex(x, check_errors=False).inverse
 
 
+_INVERSE_KERNEL_OK: Dict[int, bool] = {}
+
+
+def inverse4x4(*mats: torch.Tensor):
+    """Inverses of up to three equally shaped (..., 4, 4) fp32 CUDA tensors in ONE launch
+    (``sgv3d_inverse4x4``: the rounding sequence of torch's CUDA ``inverse``, restated)."""
+    assert 1 <= len(mats) <= 3
+    a = [m.contiguous() for m in mats]
+    n = a[0].numel() // 16
+    out = torch.empty((len(a),) + tuple(a[0].shape), dtype=torch.float32, device=a[0].device)
+    ptrs = [N.ptr(t) for t in a] + [0] * (3 - len(a))
+    outs = [N.ptr(out[i]) for i in range(len(a))] + [0] * (3 - len(a))
+    with torch.cuda.device(a[0].device):
+        N.check(N.lib().sgv3d_inverse4x4(n, *ptrs, *outs, N.current_stream()))
+    return tuple(out[i] for i in range(len(a)))
+
+
+def _inverse_kernel_verified(device) -> bool:
+    """One-time check per device that ``sgv3d_inverse4x4`` reproduces this installation's
+    ``torch.linalg.inv_ex`` bit for bit (it restates cuBLAS' batched LU / solve arithmetic, which a different
+    library version could change); on any difference the torch routine stays in use."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ok = _INVERSE_KERNEL_OK.get(idx)
+    if ok is None:
+        if torch.cuda.is_current_stream_capturing():
+            return False          # decided by the first eager call
+        g = torch.Generator().manual_seed(20260607)
+        a = torch.randn(384, 4, 4, generator=g)
+        a[:128] += 4.0 * torch.eye(4)
+        a[128:256] *= torch.tensor([1e-2, 1.0, 30.0, 2e3]).view(1, 1, 4)
+        a[256:320, 3] = torch.tensor([0.0, 0.0, 0.0, 1.0])        # affine, like every calibration matrix
+        a = a.to(device)
+        want = _inverse(a)
+        (got,) = inverse4x4(a)
+        ok = bool(torch.equal(want.view(torch.int32), got.view(torch.int32)))
+        _INVERSE_KERNEL_OK[idx] = ok
+        if not ok:
+            import warnings
+            warnings.warn("sgv3d_inverse4x4 differs from torch.linalg.inv_ex on this installation; "
+                          "using torch's routine for the per-camera inverses")
+    return ok
+
+
 def camera_matrices(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat):
     """``ida.inverse()``, ``sensor2virtual @ inverse(intrin)``, ``sensor2ego @ inverse(sensor2virtual)``
     evaluated with the reference's own torch routines (lss_fpn.py:392,361,367), shapes (B, Nc, 4, 4)."""
-    if ida_mat.is_cuda and ida_mat.shape == intrin_mat.shape == sensor2virtual_mat.shape and ida_mat.dim() >= 3:
+    same = ida_mat.shape == intrin_mat.shape == sensor2virtual_mat.shape and ida_mat.dim() >= 3
+    if ida_mat.is_cuda and same and ida_mat.numel() > 0 and \
+            ida_mat.dtype == intrin_mat.dtype == sensor2virtual_mat.dtype == torch.float32 and \
+            _inverse_kernel_verified(ida_mat.device):
+        # the three batched LU inverses of the reference (lss_fpn.py:392,361,367) in one launch instead of torch's
+        # cat + getrf + laswp + 2 x trsm + identity / pivot set-up kernels; bit-identical (verified above and by
+        # tests/test_gpu_lift_splat.py::test_inverse4x4_kernel_is_bit_identical_to_torch)
+        ida_inv, intrin_inv, s2v_inv = inverse4x4(ida_mat, intrin_mat, sensor2virtual_mat)
+    elif ida_mat.is_cuda and same:
         # one batched LU for the three inverses instead of three: the batched routine treats every 4x4
         # independently, so each inverse keeps the bits of its own call (tools/probe_prep.py;
         # tests/test_gpu_lift_splat.py::test_stacked_inverse_is_bit_identical) at a third of the launches.

@@ -352,3 +352,31 @@ def test_fused_bsm_assembly_is_bit_identical_to_the_torch_assembly(shape_name, b
     hl = height_logits.clone().requires_grad_(True)
     via_autograd = mod.forward_single_sweep_bsm(hl, semantic_logits, context, md)
     assert torch.equal(via_autograd.detach(), want)
+
+
+def test_inverse4x4_kernel_is_bit_identical_to_torch():
+    """sgv3d_inverse4x4 restates the arithmetic of torch.inverse on CUDA (the call the reference makes at
+    lss_fpn.py:361,367,392): every bit of every inverse must agree, for calibration matrices of both families,
+    random BDA, matrices that need row pivoting and badly scaled ones."""
+    from sgv3d_b200.view_transform import _inverse_kernel_verified, camera_matrices, inverse4x4
+    dev = torch.device("cuda", 0)
+    assert _inverse_kernel_verified(dev)
+    sets = []
+    for fam in ("dair_r50", "rope3d_r50"):
+        m = make_mats(get_shape(fam), 200, 1, seed=61, bda="random")
+        sets += [m["ida"], m["intrin"], m["sensor2virtual"], m["sensor2ego"], m["bda"].unsqueeze(1)]
+    g = torch.Generator().manual_seed(3)
+    rnd = torch.randn(4096, 1, 4, 4, generator=g)
+    sets += [rnd, rnd * torch.logspace(-3, 3, 4).view(1, 1, 1, 4), rnd[:, :, [2, 0, 3, 1]] + torch.eye(4)]
+    for a in sets:
+        a = a.float().cuda()
+        want = torch.inverse(a)
+        (got,) = inverse4x4(a)
+        assert torch.equal(want.view(torch.int32), got.view(torch.int32))
+    # three sets in one launch, as camera_matrices uses it, against the reference's three separate calls
+    m = make_mats(get_shape("dair_r50"), 37, 2, seed=62, bda=None)
+    ida, k, s2v, s2e = (m[n].cuda() for n in ("ida", "intrin", "sensor2virtual", "sensor2ego"))
+    ida_inv, mv, me = camera_matrices(s2e, s2v, k, ida)
+    assert torch.equal(ida_inv, ida.inverse())
+    assert torch.equal(mv, s2v.matmul(torch.inverse(k)))
+    assert torch.equal(me, s2e.matmul(torch.inverse(s2v)))
