@@ -126,6 +126,17 @@ SGV3D_API int sgv3d_geometry_quantize(int arith, int B, int Nc, int D, int fH, i
 SGV3D_API int sgv3d_inverse4x4(int n, const float *a0, const float *a1, const float *a2, float *inv0,
                      float *inv1, float *inv2, sgv3d_stream_t stream);
 
+/* The whole per-camera 4x4 prep of lss_fpn.py:361,367,392 in one launch (n cameras, row-major fp32):
+ *   ida_inv   = inverse(ida)
+ *   m_virtual = sensor2virtual @ inverse(intrin)
+ *   m_ego     = sensor2ego @ inverse(sensor2virtual)
+ * inverses as sgv3d_inverse4x4; the products in the rounding order torch's CUDA matmul uses for these
+ * batches (tools/probe_matmul.py): product_arith = SGV3D_ARITH_SEQ for a single matrix, SGV3D_ARITH_FMA
+ * (k-ascending FMA chain) for two or more.  The Python host verifies both against torch before relying on them. */
+SGV3D_API int sgv3d_camera_prep(int n, int product_arith, const float *ida, const float *intrin,
+                      const float *sensor2virtual, const float *sensor2ego, float *ida_inv,
+                      float *m_virtual, float *m_ego, sgv3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) fused lift-splat.  The plan (index) depends only on calibration + grid; forward/backward
  *     (values) depend on the activations.  Static roadside cameras can build the plan once.

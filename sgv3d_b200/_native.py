@@ -21,7 +21,7 @@ SYMBOLS = (
     "sgv3d_abi_version", "sgv3d_last_error", "sgv3d_launch_count",
     "sgv3d_voxel_pooling_workspace_bytes", "sgv3d_voxel_pooling_forward",
     "sgv3d_voxel_pooling_backward_workspace_bytes", "sgv3d_voxel_pooling_backward",
-    "sgv3d_geometry_quantize", "sgv3d_inverse4x4",
+    "sgv3d_geometry_quantize", "sgv3d_inverse4x4", "sgv3d_camera_prep",
     "sgv3d_lift_splat_workspace_bytes", "sgv3d_lift_splat_plan", "sgv3d_lift_splat_forward",
     "sgv3d_lift_splat_forward_bsm", "sgv3d_lift_splat_backward", "sgv3d_lift_splat_plan_expand",
     "sgv3d_profile_enable", "sgv3d_profile_report",
@@ -69,6 +69,8 @@ def lib() -> ctypes.CDLL:
     L.sgv3d_geometry_quantize.argtypes = [c_int] * 6 + [c_void_p] * 13
     L.sgv3d_inverse4x4.restype = c_int
     L.sgv3d_inverse4x4.argtypes = [c_int] + [c_void_p] * 7
+    L.sgv3d_camera_prep.restype = c_int
+    L.sgv3d_camera_prep.argtypes = [c_int, c_int] + [c_void_p] * 8
     P = ctypes.POINTER(LiftSplatDesc)
     L.sgv3d_lift_splat_workspace_bytes.restype = c_size_t
     L.sgv3d_lift_splat_workspace_bytes.argtypes = [P]

@@ -58,21 +58,24 @@ geometry_quantize_kernel(int Nc, int D, int fH, int fW, const float *__restrict_
 // One thread per matrix (a batch holds a few hundred of them); everything in registers.
 // The host side checks the kernel against torch's own routine once per process and device before using it.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-inverse4x4_kernel(const float *__restrict__ in0, const float *__restrict__ in1, const float *__restrict__ in2,
-                  float *__restrict__ out0, float *__restrict__ out1, float *__restrict__ out2, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float *in = blockIdx.y == 0 ? in0 : (blockIdx.y == 1 ? in1 : in2);
-  float *out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
-  float a[4][4], x[4][4];
+__device__ __forceinline__ void load4x4(const float *p, float (&a)[4][4]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const float4 v = *reinterpret_cast<const float4 *>(in + (size_t)i * 16 + 4 * r);
+    const float4 v = *reinterpret_cast<const float4 *>(p + 4 * r);
     a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w;
+  }
+}
+__device__ __forceinline__ void store4x4(float *p, const float (&x)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) *reinterpret_cast<float4 *>(p + 4 * r) = make_float4(x[r][0], x[r][1], x[r][2], x[r][3]);
+}
+
+// x = inverse(a); a is overwritten with its LU factors
+__device__ __forceinline__ void invert4x4(float (&a)[4][4], float (&x)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) x[r][c] = r == c ? 1.0f : 0.0f;
-  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     // pivot: first row i >= k with the largest |a_ik|; the row swap is applied to A and to the right-hand side
@@ -117,9 +120,54 @@ inverse4x4_kernel(const float *__restrict__ in0, const float *__restrict__ in1, 
 #pragma unroll
     for (int c = 0; c < 4; ++c) x[r][c] = __fdiv_rn(x[r][c], a[r][r]);
   }
+}
+
+__global__ void __launch_bounds__(128)
+inverse4x4_kernel(const float *__restrict__ in0, const float *__restrict__ in1, const float *__restrict__ in2,
+                  float *__restrict__ out0, float *__restrict__ out1, float *__restrict__ out2, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *in = blockIdx.y == 0 ? in0 : (blockIdx.y == 1 ? in1 : in2);
+  float *out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
+  float a[4][4], x[4][4];
+  load4x4(in + (size_t)i * 16, a);
+  invert4x4(a, x);
+  store4x4(out + (size_t)i * 16, x);
+}
+
+// c = a @ b with the k-ascending rounding order torch's CUDA matmul uses for these 4x4 batches
+// (tools/probe_matmul.py): one matrix -> plain products and sums (SEQ); two or more -> FMA chain.
+template <int ARITH>
+__device__ __forceinline__ void matmul4x4(const float (&a)[4][4], const float (&b)[4][4], float (&c)[4][4]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r)
-    *reinterpret_cast<float4 *>(out + (size_t)i * 16 + 4 * r) = make_float4(x[r][0], x[r][1], x[r][2], x[r][3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[r][j] = geom::dot4<ARITH>(a[r], b[0][j], b[1][j], b[2][j], b[3][j]);
+}
+
+// The whole per-camera prep of lss_fpn.py:361,367,392 in one launch, one thread per camera:
+//   ida_inv = inverse(ida);  m_virtual = sensor2virtual @ inverse(intrin);  m_ego = sensor2ego @ inverse(sensor2virtual)
+template <int ARITH>
+__global__ void __launch_bounds__(128)
+camera_prep_kernel(int n, const float *__restrict__ ida, const float *__restrict__ intrin,
+                   const float *__restrict__ s2v, const float *__restrict__ s2e, float *__restrict__ ida_inv,
+                   float *__restrict__ m_virtual, float *__restrict__ m_ego) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t o = (size_t)i * 16;
+  float a[4][4], x[4][4], v[4][4], c[4][4];
+  load4x4(ida + o, a);
+  invert4x4(a, x);
+  store4x4(ida_inv + o, x);
+  load4x4(intrin + o, a);
+  invert4x4(a, x);
+  load4x4(s2v + o, v);
+  matmul4x4<ARITH>(v, x, c);
+  store4x4(m_virtual + o, c);
+  invert4x4(v, x);        // v becomes its LU factors
+  load4x4(s2e + o, a);
+  matmul4x4<ARITH>(a, x, c);
+  store4x4(m_ego + o, c);
 }
 
 }  // namespace
@@ -141,6 +189,31 @@ extern "C" int sgv3d_inverse4x4(int n, const float *a0, const float *a1, const f
   prof_begin(s);
   inverse4x4_kernel<<<dim3(ceil_div(n, 128), sets), 128, 0, s>>>(a0, a1, a2, inv0, inv1, inv2, n);
   SGV3D_CHECK_LAUNCH("inverse4x4_kernel");
+  return SGV3D_OK;
+}
+
+extern "C" int sgv3d_camera_prep(int n, int product_arith, const float *ida, const float *intrin,
+                                 const float *sensor2virtual, const float *sensor2ego, float *ida_inv,
+                                 float *m_virtual, float *m_ego, sgv3d_stream_t stream) {
+  using namespace sgv3d;
+  SGV3D_REQUIRE(n >= 0, "camera_prep: bad count");
+  if (n == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(product_arith == SGV3D_ARITH_SEQ || product_arith == SGV3D_ARITH_FMA,
+                "camera_prep: product_arith must be SEQ or FMA");
+  SGV3D_REQUIRE(ida && intrin && sensor2virtual && sensor2ego && ida_inv && m_virtual && m_ego,
+                "camera_prep: null pointer");
+  for (const void *q : {(const void *)ida, (const void *)intrin, (const void *)sensor2virtual,
+                        (const void *)sensor2ego, (const void *)ida_inv, (const void *)m_virtual, (const void *)m_ego})
+    SGV3D_REQUIRE(reinterpret_cast<uintptr_t>(q) % 16 == 0, "camera_prep: matrices must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
+  if (product_arith == SGV3D_ARITH_FMA)
+    camera_prep_kernel<SGV3D_ARITH_FMA><<<ceil_div(n, 128), 128, 0, s>>>(n, ida, intrin, sensor2virtual, sensor2ego,
+                                                                        ida_inv, m_virtual, m_ego);
+  else
+    camera_prep_kernel<SGV3D_ARITH_SEQ><<<ceil_div(n, 128), 128, 0, s>>>(n, ida, intrin, sensor2virtual, sensor2ego,
+                                                                        ida_inv, m_virtual, m_ego);
+  SGV3D_CHECK_LAUNCH("camera_prep_kernel");
   return SGV3D_OK;
 }
 

@@ -105,10 +105,61 @@ def _inverse_kernel_verified(device) -> bool:
     return ok
 
 
+_CAMERA_PREP_OK: Dict[tuple, bool] = {}
+
+
+def _camera_prep(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat):
+    """``sgv3d_camera_prep``: the three inverses and the two products of lss_fpn.py:361,367,392 in one launch."""
+    shape = tuple(ida_mat.shape)
+    n = ida_mat.numel() // 16
+    out = torch.empty((3,) + shape, dtype=torch.float32, device=ida_mat.device)
+    a = [t.contiguous() for t in (ida_mat, intrin_mat, sensor2virtual_mat, sensor2ego_mat)]
+    with torch.cuda.device(ida_mat.device):
+        N.check(N.lib().sgv3d_camera_prep(n, N.ARITH_SEQ if n == 1 else N.ARITH_FMA, *[N.ptr(t) for t in a],
+                                          N.ptr(out[0]), N.ptr(out[1]), N.ptr(out[2]), N.current_stream()))
+    return out[0], out[1], out[2]
+
+
+def _camera_prep_verified(device, shape) -> bool:
+    """One-time check per device and batch shape that the fused prep kernel reproduces torch's ``inverse`` and
+    batched ``matmul`` bit for bit (torch picks its matmul kernel, and with it the rounding order, by batch count:
+    tools/probe_matmul.py); on any difference the torch calls stay in use."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, tuple(shape))
+    ok = _CAMERA_PREP_OK.get(key)
+    if ok is None:
+        if torch.cuda.is_current_stream_capturing():
+            return False          # decided by the first eager call
+        if not _inverse_kernel_verified(device):
+            _CAMERA_PREP_OK[key] = False
+            return False
+        g = torch.Generator().manual_seed(20260608)
+        ok = True
+        for rep in range(4):     # small batches hold few matrices: several draws
+            mats = []
+            for k in range(4):
+                a = torch.randn(*shape, generator=g) + 3.0 * torch.eye(4)
+                a[..., 3, :] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+                mats.append(a.to(device))
+            ida, intrin, s2v, s2e = mats
+            want = (_inverse(ida), s2v.matmul(_inverse(intrin)), s2e.matmul(_inverse(s2v)))
+            got = _camera_prep(s2e, s2v, intrin, ida)
+            ok = ok and all(torch.equal(w.view(torch.int32), g_.view(torch.int32)) for w, g_ in zip(want, got))
+        ok = bool(ok)
+        _CAMERA_PREP_OK[key] = ok
+    return ok
+
+
 def camera_matrices(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat):
     """``ida.inverse()``, ``sensor2virtual @ inverse(intrin)``, ``sensor2ego @ inverse(sensor2virtual)``
     evaluated with the reference's own torch routines (lss_fpn.py:392,361,367), shapes (B, Nc, 4, 4)."""
     same = ida_mat.shape == intrin_mat.shape == sensor2virtual_mat.shape and ida_mat.dim() >= 3
+    f32 = ida_mat.dtype == intrin_mat.dtype == sensor2virtual_mat.dtype == sensor2ego_mat.dtype == torch.float32
+    if ida_mat.is_cuda and same and f32 and sensor2ego_mat.shape == ida_mat.shape and ida_mat.numel() > 0 and \
+            _camera_prep_verified(ida_mat.device, ida_mat.shape):
+        # inverses AND products in one launch, bit-identical to the torch calls of the reference (verified above
+        # and by tests/test_gpu_lift_splat.py::test_camera_prep_kernel_is_bit_identical_to_torch)
+        return _camera_prep(sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat)
     if ida_mat.is_cuda and same and ida_mat.numel() > 0 and \
             ida_mat.dtype == intrin_mat.dtype == sensor2virtual_mat.dtype == torch.float32 and \
             _inverse_kernel_verified(ida_mat.device):

@@ -380,3 +380,18 @@ def test_inverse4x4_kernel_is_bit_identical_to_torch():
     assert torch.equal(ida_inv, ida.inverse())
     assert torch.equal(mv, s2v.matmul(torch.inverse(k)))
     assert torch.equal(me, s2e.matmul(torch.inverse(s2v)))
+
+
+@pytest.mark.parametrize("batch,num_cams", [(1, 1), (2, 1), (1, 3), (7, 1), (32, 1), (64, 2)])
+def test_camera_prep_kernel_is_bit_identical_to_torch(batch, num_cams):
+    """sgv3d_camera_prep (three inverses + two products, one launch) == the reference's torch calls
+    (lss_fpn.py:361,367,392) bit for bit, for every batch count (torch's matmul changes its rounding order between a
+    single matrix and a batch)."""
+    from sgv3d_b200.view_transform import _camera_prep, _camera_prep_verified, camera_matrices
+    m = make_mats(get_shape("rope3d_r50"), batch, num_cams, seed=70 + batch, bda=None)
+    ida, k, s2v, s2e = (m[n].cuda() for n in ("ida", "intrin", "sensor2virtual", "sensor2ego"))
+    assert _camera_prep_verified(ida.device, ida.shape)
+    want = (ida.inverse(), s2v.matmul(torch.inverse(k)), s2e.matmul(torch.inverse(s2v)))
+    for got in (_camera_prep(s2e, s2v, k, ida), camera_matrices(s2e, s2v, k, ida)):
+        for w, g in zip(want, got):
+            assert torch.equal(w.view(torch.int32), g.contiguous().view(torch.int32))
