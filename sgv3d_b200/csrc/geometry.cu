@@ -145,29 +145,28 @@ __device__ __forceinline__ void matmul4x4(const float (&a)[4][4], const float (&
     for (int j = 0; j < 4; ++j) c[r][j] = geom::dot4<ARITH>(a[r], b[0][j], b[1][j], b[2][j], b[3][j]);
 }
 
-// The whole per-camera prep of lss_fpn.py:361,367,392 in one launch, one thread per camera:
-//   ida_inv = inverse(ida);  m_virtual = sensor2virtual @ inverse(intrin);  m_ego = sensor2ego @ inverse(sensor2virtual)
+// The whole per-camera prep of lss_fpn.py:361,367,392 in one launch; blockIdx.y selects one of the three
+// independent tasks of a camera (so that their latency chains run side by side):
+//   0: ida_inv = inverse(ida)   1: m_virtual = sensor2virtual @ inverse(intrin)   2: m_ego = sensor2ego @ inverse(sensor2virtual)
 template <int ARITH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 camera_prep_kernel(int n, const float *__restrict__ ida, const float *__restrict__ intrin,
                    const float *__restrict__ s2v, const float *__restrict__ s2e, float *__restrict__ ida_inv,
                    float *__restrict__ m_virtual, float *__restrict__ m_ego) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t o = (size_t)i * 16;
-  float a[4][4], x[4][4], v[4][4], c[4][4];
-  load4x4(ida + o, a);
+  const int task = blockIdx.y;
+  float a[4][4], x[4][4], l[4][4], c[4][4];
+  load4x4((task == 0 ? ida : (task == 1 ? intrin : s2v)) + o, a);
+  if (task != 0) load4x4((task == 1 ? s2v : s2e) + o, l);   // left factor of the product, in flight during the LU
   invert4x4(a, x);
-  store4x4(ida_inv + o, x);
-  load4x4(intrin + o, a);
-  invert4x4(a, x);
-  load4x4(s2v + o, v);
-  matmul4x4<ARITH>(v, x, c);
-  store4x4(m_virtual + o, c);
-  invert4x4(v, x);        // v becomes its LU factors
-  load4x4(s2e + o, a);
-  matmul4x4<ARITH>(a, x, c);
-  store4x4(m_ego + o, c);
+  if (task == 0) {
+    store4x4(ida_inv + o, x);
+  } else {
+    matmul4x4<ARITH>(l, x, c);
+    store4x4((task == 1 ? m_virtual : m_ego) + o, c);
+  }
 }
 
 }  // namespace
@@ -208,11 +207,11 @@ extern "C" int sgv3d_camera_prep(int n, int product_arith, const float *ida, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
   if (product_arith == SGV3D_ARITH_FMA)
-    camera_prep_kernel<SGV3D_ARITH_FMA><<<ceil_div(n, 128), 128, 0, s>>>(n, ida, intrin, sensor2virtual, sensor2ego,
-                                                                        ida_inv, m_virtual, m_ego);
+    camera_prep_kernel<SGV3D_ARITH_FMA><<<dim3(ceil_div(n, 64), 3), 64, 0, s>>>(n, ida, intrin, sensor2virtual, sensor2ego,
+                                                                               ida_inv, m_virtual, m_ego);
   else
-    camera_prep_kernel<SGV3D_ARITH_SEQ><<<ceil_div(n, 128), 128, 0, s>>>(n, ida, intrin, sensor2virtual, sensor2ego,
-                                                                        ida_inv, m_virtual, m_ego);
+    camera_prep_kernel<SGV3D_ARITH_SEQ><<<dim3(ceil_div(n, 64), 3), 64, 0, s>>>(n, ida, intrin, sensor2virtual, sensor2ego,
+                                                                               ida_inv, m_virtual, m_ego);
   SGV3D_CHECK_LAUNCH("camera_prep_kernel");
   return SGV3D_OK;
 }

@@ -3,7 +3,7 @@ B=${1:-64}
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; tail -2 gpurun_out/bench_tmp.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"ls_|inverse4x4" -s 19 -c 9 -o gpurun_out/full -f python tools/prof_step.py --batch $B --steps 3 --backward > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:"ls_|camera_prep|inverse4x4" -s 23 -c 9 -o gpurun_out/full -f python tools/prof_step.py --batch $B --steps 3 --backward > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_tmp.json"))
