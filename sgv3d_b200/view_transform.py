@@ -7,9 +7,10 @@ Reference call sites (relative to the reference repository root):
   layers/backbones/lss_fpn.py:281-294       registered buffers (voxel_size/coord/num, frustum)
   layers/backbones/lss_fpn.py:325-401       create_frustum / height2localtion / get_geometry
 
-The per-camera 4x4 products are kept in PyTorch with the same calls as the reference so the 16
-floats per matrix that enter the per-point arithmetic are identical (SURVEY.md §7 hard part 1);
-everything per point / per pixel / per voxel happens in the sm_100a kernels.
+The per-camera 4x4 prep (three inverses, two products: lss_fpn.py:361,367,392) runs in one library kernel that
+restates torch's CUDA arithmetic bit for bit (verified against the torch calls at first use, which remain the
+fallback), so the 16 floats per matrix that enter the per-point arithmetic are identical to the reference's
+(SURVEY.md §7 hard part 1); everything per point / per pixel / per voxel happens in the sm_100a kernels.
 """
 from __future__ import annotations
 
@@ -577,7 +578,7 @@ class LiftSplatGraph:
 
     The whole per-step sequence -- the reference's per-camera 4x4 products (lss_fpn.py:361,367,392), the
     plan kernels and the forward kernels -- is captured once and re-launched with a single
-    ``cudaGraphLaunch``: the ~25 small launches of a step otherwise cost more host time than the GPU
+    ``cudaGraphLaunch``: the seven launches of a step otherwise cost about as much host time as the GPU
     needs to run them.  Inference only (no autograd).  The captured graph reads the tensors handed to
     the constructor (``height_feature`` and every entry of ``mats_dict``); ``__call__`` optionally
     copies new values into them first, and returns the (B, C, Y, X) BEV map, which is overwritten by
@@ -607,7 +608,7 @@ class LiftSplatGraph:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(max(1, warmup)):   # lazy initialisation (cuBLAS handles, smem attributes) before capture
+            for _ in range(max(1, warmup)):   # lazy initialisation (one-time self-checks, smem attributes) before capture
                 step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
