@@ -36,6 +36,17 @@ def test_workspace_queries_and_argument_validation():
         N.check(rc)
     # B == 0 is a no-op that must not touch the device
     assert L.sgv3d_geometry_quantize(0, 0, 1, 4, 3, 5, 1, 1, 1, 1, 1, 1, 0, 1, lo, sz, 0, 0, 0) == 0
+    # the 4x4 prep entry points validate before they launch
+    assert L.sgv3d_inverse4x4(-1, 0, 0, 0, 0, 0, 0, 0) == 1 and b"bad count" in L.sgv3d_last_error()
+    assert L.sgv3d_inverse4x4(0, 0, 0, 0, 0, 0, 0, 0) == 0
+    assert L.sgv3d_inverse4x4(4, 16, 0, 32, 48, 0, 64, 0) == 1 and b"pair up" in L.sgv3d_last_error()
+    assert L.sgv3d_inverse4x4(4, 16, 0, 0, 40, 0, 0, 0) == 1 and b"aligned" in L.sgv3d_last_error()
+    assert L.sgv3d_camera_prep(4, N.ARITH_PAIR, 16, 32, 48, 64, 80, 96, 112, 0) == 1
+    assert b"SEQ or FMA" in L.sgv3d_last_error()
+    assert L.sgv3d_camera_prep(0, N.ARITH_FMA, 0, 0, 0, 0, 0, 0, 0, 0) == 0
+    d2 = N.LiftSplatDesc(B=1, Nc=1, D=90, fH=54, fW=96, C=87, X=128, Y=128, Z=1, arith=0, ctx_dtype=0)
+    assert L.sgv3d_lift_splat_forward_bsm(d2, 16, 16, 16, 87, 0, 0.45, 16, 16, 0, 0) == 1
+    assert b"semantic_channels" in L.sgv3d_last_error()
     # too-small workspace is reported, not written past
     rc = L.sgv3d_voxel_pooling_forward(1, 100, 8, 4, 4, 1, 1, 1, 1, 0, 1, 16, 0)
     assert rc == 2 and b"workspace" in L.sgv3d_last_error()
