@@ -361,6 +361,14 @@ def run_ours(args):
         "dominant_kernel": dominant, "dominant_share": kern[dominant]["share"] if dominant else None,
         "kernels": kern,
     }
+    if "ls_reduce_kernel" in kern:
+        # the dominant kernel on its own: it must read every context row once and write the BEV map once
+        rb = (4 * shape.channels * shape.fH * shape.fW + 4 * shape.channels * shape.grid[0] * shape.grid[1]) * B
+        ra = rb / (kern["ls_reduce_kernel"]["avg_us"] * 1e-6) / 1e9
+        roofline["dominant_kernel_roofline"] = {
+            "kernel": "ls_reduce_kernel", "algorithmic_bytes_per_launch": rb, "launch_us": kern["ls_reduce_kernel"]["avg_us"],
+            "achieved": ra, "unit": "GB/s", "frac": ra / peak,
+            "note": "context rows read once + BEV written once; the event-timed launch includes ~5 us of launch gap"}
     cpu = None
     if world == 1:
         fps, n, cores, total = cpu_reference_run(shape, 2000, 2, budget_s=12.0)
