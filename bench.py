@@ -184,6 +184,10 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
+    if world > 1:
+        from sgv3d_b200.sharding import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)   # pinned staging buffers local to the GPU's PCIe root
     if world > 1:
         import torch.distributed as dist
         # NCCL prints its version banner on stdout at the first collective; stdout carries exactly one JSON line,
@@ -385,7 +389,8 @@ def run_ours(args):
                    "C": shape.channels, "grid": list(shape.grid), "arith": "PAIR (torch-CUDA bmm order)",
                    "l2": f"working set per step ({(in_bytes + out_bytes) / 1e6:.0f} MB in+out, 2 rotating input "
                          f"sets) exceeds the 126 MB L2",
-                   "sharding": "frames across ranks, no collective (replicas only)"},
+                   "sharding": "frames across ranks, no collective (replicas only)",
+                   "numa": "rank 0 bound to node %s" % numa_node if numa_node is not None else "not bound"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K,

@@ -13,7 +13,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-__all__ = ["shard_bounds", "shard_mats", "shard_frames", "max_over_ranks", "sum_over_ranks"]
+__all__ = ["shard_bounds", "shard_mats", "shard_frames", "max_over_ranks", "sum_over_ranks", "bind_to_gpu_numa_node"]
 
 # keys of the reference's ``mats_dict`` (dataset/nusc_mv_det_dataset.py:864-871) and their frame axis
 _PER_FRAME_KEYS = ("sensor2ego_mats", "sensor2virtual_mats", "intrin_mats", "ida_mats", "reference_heights",
@@ -68,3 +68,36 @@ def sum_over_ranks(values, group=None, device=None) -> list:
     """Element-wise sum over ranks (frames processed, kernels launched)."""
     import torch.distributed as dist
     return _reduce(values, dist.ReduceOp.SUM, group, device)
+
+
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """One process per GPU: pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned
+    host staging buffers (first touch) and the threads that fill them are local to the GPU's PCIe root.  Without
+    it every rank's buffers may land on one socket and the host<->device copies of an 8-GPU box contend for
+    the inter-socket link.  Best effort: returns the node, or None when the topology cannot be read (then
+    nothing is changed).  Call it before allocating pinned memory."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
