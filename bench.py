@@ -87,6 +87,13 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def count(self) -> int:
+        """samples written so far"""
+        try:
+            return sum(1 for _ in open(self.f.name))
+        except OSError:
+            return 0
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -266,13 +273,18 @@ def run_ours(args):
     # step loop running (untimed) for 0.4 s so that the clock / throttle samples are taken under this load
     t_ext = time.perf_counter()
     i = K
-    while time.perf_counter() - t_ext < 0.4:
+    # (nvidia-smi needs up to a second to start when eight ranks launch one each: keep the load up until it has
+    # delivered at least ten samples, three seconds at most)
+    while True:
+        el = time.perf_counter() - t_ext
+        if (el >= 0.4 and (sampler.p is None or sampler.count() >= 10)) or el >= 3.0:
+            break
         for _ in range(16):
             step(i)
             i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop()
-    clocks["span"] = "timed region + 0.4 s of the same step loop (nvidia-smi -lms 20)"
+    clocks["span"] = "timed region + >= 0.4 s of the same step loop (nvidia-smi -lms 20)"
     ms_eager = None
     if not args.eager:
         for i in range(3):
