@@ -53,7 +53,7 @@ extern "C" {
  *   FMA: fma(a3,b3, fma(a2,b2, fma(a1,b1, a0*b0)))  (k-ascending FMA chain)
  *   PAIR: fma(a1,b1, a0*b0) + fma(a3,b3, a2*b2)     (pairwise FMA: what torch's CUDA bmm -> cuBLAS
  *        does for these shapes on B200, i.e. bit-exact with the reference run on the GPU; measured
- *        by tools/probe_arith.py, see profiles/arith_probe_r01.json) */
+ *        by tests/probe_arith.py, see profiles/arith_probe_r01.json) */
 #define SGV3D_ARITH_SEQ 0
 #define SGV3D_ARITH_FMA 1
 #define SGV3D_ARITH_PAIR 2

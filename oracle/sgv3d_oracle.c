@@ -30,7 +30,7 @@
  *   ORACLE_ARITH_FMA : fma(a3,b3, fma(a2,b2, fma(a1,b1, a0*b0)))  (k-ascending FMA chain)
  *   ORACLE_ARITH_PAIR: fma(a1,b1, a0*b0) + fma(a3,b3, a2*b2)      (pairwise FMA: what torch's CUDA
  *                      bmm / cuBLAS does for these shapes on B200 -- 0 bit mismatches over
- *                      4 x 3.7M outputs per stage, tools/probe_arith.py, profiles/arith_probe_r01.json)
+ *                      4 x 3.7M outputs per stage, tests/probe_arith.py, profiles/arith_probe_r01.json)
  */
 #define ORACLE_ARITH_SEQ 0
 #define ORACLE_ARITH_FMA 1
