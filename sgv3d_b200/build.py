@@ -9,8 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsgv3d_b200.so")
-SOURCES = ["common.cu", "geometry.cu", "voxel_pooling.cu", "lift_splat.cu"]
-HEADERS = ["common.cuh", "geometry.cuh", "sort.cuh", "transpose.cuh", "../../include/sgv3d_b200.h"]
+SOURCES = ["common.cu", "geometry.cu", "voxel_pooling.cu", "lift_splat.cu", "lift_splat_block.cu"]
+HEADERS = ["common.cuh", "geometry.cuh", "sort.cuh", "transpose.cuh", "ls_shared.cuh", "ls_block.cuh",
+           "../../include/sgv3d_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",
               "--fmad=false"]

@@ -337,6 +337,68 @@ struct LinearGuard {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// LinearWalk: the same guarded linear form as LinearGuard, arranged so that ONE thread can walk the height bins
+// of a pixel at ~14 full-rate instructions per bin (pixel-block pipeline, lift_splat_block.cu).
+//   q' = fma(hgt, k, c - 0.5)          real-valued voxel coordinate minus one half (one rounding)
+//   t  = q' + 1.5 * 2^23               rounds q' to the nearest integer r (exact for |q'| < 2^22); r = floor(Q) whenever
+//                                      frac(Q) is not 0, and consecutive bins fall into the same voxel column iff their
+//                                      t are bitwise equal
+//   e  = q' - (t - 1.5 * 2^23)         exact; |e| = |frac(Q) - 0.5|: the bin is within delta of an integer (where the
+//                                      reference's fp32 chain may land on the other side) iff |e| > 0.5 - delta
+// Truncation toward zero (the reference's `.int()`) differs from floor only for Q in (-1, 0): that column is index
+// 0, so r = -1 is mapped to 0 when the index is formed (a spurious change at the 0 boundary then compares equal).
+// mode 0: the exact chain decides every bin; 1: linear form with per-bin guard; 2: every bin of the pixel is
+// provably dropped (a coordinate stays outside the grid by more than the guard band over the whole height range).
+// ---------------------------------------------------------------------------------------------
+struct LinearWalk {
+  float kx, cx, thx;  // q'_x = fma(hgt, kx, cx); unsafe iff |e_x| > thx
+  float ky, cy, thy;
+  int mode;
+
+  __device__ __forceinline__ void init(float pv0, float pv1, float pv2, const float *me, float ref_h,
+                                       float p0z_lo, float p0z_hi, const Grid &g) {
+    const double u32 = 1.9073486328125e-06;  // 32 * 2^-24
+    const double rp = 1.0 / (double)pv1;
+    const double h_lo = (double)ref_h - (double)p0z_hi, h_hi = (double)ref_h - (double)p0z_lo;
+    const double h_abs = fmax(fabs(h_lo), fabs(h_hi)) * 1.000001 + 1e-30;
+    const double rho = h_abs * fabs(rp);
+    double kap[3], S[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double t0 = (double)me[4 * r + 0] * pv0, t1 = (double)me[4 * r + 1] * pv1, t2 = (double)me[4 * r + 2] * pv2;
+      kap[r] = (t0 + t1 + t2) * rp;
+      S[r] = (fabs(t0) + fabs(t1) + fabs(t2)) * rho + fabs((double)me[4 * r + 3]);
+    }
+    const double isx = 1.0 / (double)g.size[0], isy = 1.0 / (double)g.size[1];
+    const double kxd = kap[0] * isx, cxd = ((double)me[3] - (double)g.lower[0]) * isx;
+    const double kyd = kap[1] * isy, cyd = ((double)me[7] - (double)g.lower[1]) * isy;
+    kx = (float)kxd; cx = (float)(cxd - 0.5);
+    ky = (float)kyd; cy = (float)(cyd - 0.5);
+    // guard band: 32 u (S + |lower| + size) / size (the extra `size` covers the rounding of c - 0.5)
+    const double ddx = u32 * ((S[0] + fabs((double)g.lower[0])) * isx + 1.0) + 1e-30;
+    const double ddy = u32 * ((S[1] + fabs((double)g.lower[1])) * isy + 1.0) + 1e-30;
+    thx = (float)((0.5 - ddx) * 0.9999998);
+    thy = (float)((0.5 - ddy) * 0.9999998);
+    // ranges of the real-valued coordinates over the pixel's height range (linear => the two ends decide)
+    const double qxa = kxd * h_lo + cxd, qxb = kxd * h_hi + cxd;
+    const double qya = kyd * h_lo + cyd, qyb = kyd * h_hi + cyd;
+    const double cz = (double)me[11] - (double)g.lower[2];
+    const double dz = u32 * (S[2] + fabs((double)g.lower[2])) + 1e-30;
+    const double tz_a = kap[2] * h_lo + cz, tz_b = kap[2] * h_hi + cz;
+    const bool z_in = fmin(tz_a, tz_b) - dz > (double)g.zt_lo && fmax(tz_a, tz_b) + dz < (double)g.zt_hi;
+    const bool z_out = fmax(tz_a, tz_b) + dz < (double)g.zt_lo || fmin(tz_a, tz_b) - dz > (double)g.zt_hi;
+    const double big = fmax(fmax(fabs((double)pv0), fabs((double)pv1)), fabs((double)pv2)) * rho;
+    // every intermediate of the exact chain comfortably finite (then the error bounds hold); NaN fails a comparison
+    const bool tame = big < 1e30 && S[0] < 1e30 && S[1] < 1e30 && S[2] < 1e30 && fabs((double)pv1) > 1e-30;
+    const bool out = tame && (z_out || fmin(qxa, qxb) - ddx > (double)g.X || fmax(qxa, qxb) + ddx < -1.0 ||
+                              fmin(qya, qyb) - ddy > (double)g.Y || fmax(qya, qyb) + ddy < -1.0);
+    const double qmax = fmax(fmax(fabs(qxa), fabs(qxb)), fmax(fabs(qya), fabs(qyb)));
+    const bool lin = tame && z_in && ddx < 0.25 && ddy < 0.25 && qmax < 2.0e6;
+    mode = out ? 2 : (lin ? 1 : 0);
+  }
+};
+
 // :487-488  ((g - lower) / size).int() -- fp32 subtract, IEEE divide, cvt.rzi.s32.f32
 // (truncation toward zero, saturating, NaN -> 0: what `.int()` does on a CUDA tensor).
 __device__ __forceinline__ int quantize1(float g, float lower, float size) {

@@ -36,13 +36,14 @@
 #include <algorithm>
 
 #include "geometry.cuh"
+#include "ls_block.cuh"
+#include "ls_shared.cuh"
 #include "sort.cuh"
 #include "transpose.cuh"
 
 namespace sgv3d {
 namespace {
 
-constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
 
 // Sorted (voxel-major) entry: frame-local pixel row (n*P + p) << 6 | the voxel's index inside its 64-voxel
 // reduce tile (written by the plan), and the run weight (written by the forward weights pass through
@@ -50,22 +51,6 @@ constexpr int kChunk = 128;  // pixels per plan chunk == threads per plan CTA
 struct __align__(8) Entry {
   unsigned off;
   float w;
-};
-
-struct Dims {
-  int B, Nc, D, fH, fW, C, X, Y, Z;
-  int P;        // fH*fW pixels per camera
-  int cpc;      // chunks per camera
-  int nchunks;  // chunks per frame = Nc*cpc
-  int V;        // X*Y voxels per frame
-  int Cpad;     // padded row length of the channels-last copies (elements) = G*(4*NV + NS)
-  int G, NV;    // row layout: G lanes per row, NV 4-element vectors per lane (transpose.cuh)
-  int esize;    // bytes per context element (4 fp32, 2 bf16)
-  int cap;      // max runs per frame (= ELL slots per frame)
-  int ntiles;   // ceil(V / 64) reduce tiles per frame
-  int logits;             // height tensor holds raw logits (softmax over D fused)
-  long long hs, cs;       // element strides between consecutive cameras of height / context
-  long long ghs, gcs;     // same for grad_height / grad_context
 };
 
 // Run in its tile bucket (after the MSD pass, before the per-tile finish).
@@ -82,34 +67,6 @@ struct Workspace {
   void *ctxT;
   size_t bytes;
 };
-
-// Row layout by channel count: a G-lane group owns a whole channels-last row, NV 4-element vectors per
-// lane (Cpad = 4*G*NV = 16*G*NV bytes in fp32: rows start on 64-byte boundaries, no padding at C = 80).
-void pick_row_cfg(int C, int *G, int *NV) {
-  if (C <= 192) { *G = 8; *NV = ceil_div(C, 32); }
-  else { *G = 16; *NV = ceil_div(C, 64); }
-}
-
-Dims make_dims(const sgv3d_lift_splat_desc *d) {
-  Dims m;
-  m.B = d->B; m.Nc = d->Nc; m.D = d->D; m.fH = d->fH; m.fW = d->fW; m.C = d->C;
-  m.X = d->X; m.Y = d->Y; m.Z = d->Z;
-  m.P = m.fH * m.fW;
-  m.cpc = ceil_div(m.P, kChunk);
-  m.nchunks = m.Nc * m.cpc;
-  m.V = m.X * m.Y;
-  pick_row_cfg(m.C, &m.G, &m.NV);
-  m.Cpad = 4 * m.G * m.NV;
-  m.esize = d->ctx_dtype == SGV3D_DTYPE_BF16 ? 2 : 4;
-  m.cap = m.nchunks * kChunk * m.D;
-  m.ntiles = ceil_div(m.V, 64);
-  m.logits = d->height_is_logits;
-  m.hs = d->height_batch_stride ? d->height_batch_stride : (long long)m.D * m.P;
-  m.cs = d->ctx_batch_stride ? d->ctx_batch_stride : (long long)m.C * m.P;
-  m.ghs = d->grad_height_batch_stride ? d->grad_height_batch_stride : (long long)m.D * m.P;
-  m.gcs = d->grad_ctx_batch_stride ? d->grad_ctx_batch_stride : (long long)m.C * m.P;
-  return m;
-}
 
 RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 4 ? 2 : (m.G == 8 ? 3 : 4), m.Cpad}; }
 
@@ -136,24 +93,6 @@ Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   w.gctxT = c.take<float>(rows * gpad);
   w.bytes = c.used();
   return w;
-}
-
-// ---- cp.async: global -> shared copies that do not pass through registers ------------------------
-__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
-__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
 
 __device__ __forceinline__ size_t ell_slot(int frame_chunk, int D, int r, int t) {
@@ -362,7 +301,6 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
 //   tile_ptr[tile]    <- number of runs in tiles < tile;  tile_ptr[ntiles] = runs of the frame
 // grid (B), 1024 threads.  Thread = tile for the chunk walk (coalesced rows, 8 loads in flight).
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxTiles = 4096;  // V <= 262144 voxels per frame (512 x 512)
 constexpr int kScanThreads = 1024;
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -736,19 +674,6 @@ __device__ __forceinline__ void stage_columns(float *col, const float *__restric
   __syncthreads();
 }
 
-// exp(x) through the hardware 2^t unit (MUFU.EX2) with a compensated argument: t = x * log2(e) is formed as
-// t_hi + t_lo (t_hi the rounded leading product, t_lo its exact residual plus the low part of log2(e)), and
-// 2^(t_hi + t_lo) = 2^t_hi * (1 + t_lo ln 2) to first order (|t_lo| < 2^-20 for |x| < 100).  Error ~2 ulp
-// (ex2.approx's own 2^-22.5 bound), i.e. libm expf's accuracy class at a third of its instructions.
-__device__ __forceinline__ float exp_ex2(float x) {
-  const float kHi = 1.44269502162933349609375f, kLo = 1.925963033500011e-8f, kLn2 = 0.693147182464599609375f;
-  const float t_hi = __fmul_rn(x, kHi);
-  const float t_lo = __fmaf_rn(x, kLo, __fmaf_rn(x, kHi, -t_hi));
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t_hi));
-  return x < -104.0f ? 0.0f : __fmaf_rn(r, __fmul_rn(t_lo, kLn2), r);  // exp(-inf) = 0; NaN propagates
-}
-
 // Softmax over D of this thread's staged column (torch.softmax within fp32 rounding:
 // exp(x - max) / sum).  Leaves the un-normalised exponentials in col and returns 1 / sum, so the
 // normalisation costs one multiply per run / per output instead of a pass over the column.
@@ -1033,20 +958,6 @@ struct RowLd<__nv_bfloat16> {
     v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
   }
 };
-
-// acc.{0,1} = w * {x0,x1} + acc.{0,1}: one packed FFMA2 (sm_100 fma.rn.f32x2); each half rounds
-// exactly like a scalar fma.rn.
-__device__ __forceinline__ void fma2(float &a0, float &a1, float w, float x0, float x1) {
-  unsigned long long A, X, W;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(X) : "f"(x0), "f"(x1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(W) : "f"(w), "f"(w));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(A) : "l"(W), "l"(X), "l"(A));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
-}
-__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 
 // Byte offset of the 16-byte chunk j (4 voxels) of channel row r inside one 32-voxel box of the
 // tile: 128-byte rows, chunk index XOR-ed with (row & 7) -- the TMA SWIZZLE_128B pattern -- so that
@@ -1677,46 +1588,11 @@ ls_expand_kernel(Dims m, const float *__restrict__ height, int vec16, const int 
   }
 }
 
-int validate(const sgv3d_lift_splat_desc *d, const char *who) {
-  SGV3D_REQUIRE(d != nullptr, "%s: desc is null", who);
-  SGV3D_REQUIRE(d->B >= 0 && d->Nc > 0 && d->D > 0 && d->fH > 0 && d->fW > 0 && d->C > 0 && d->X > 0 &&
-                    d->Y > 0 && d->Z > 0, "%s: bad sizes", who);
-  SGV3D_REQUIRE(d->B <= 65535, "%s: B > 65535", who);
-  SGV3D_REQUIRE(d->D <= 400, "%s: D=%d > 400 unsupported (height columns are staged in shared memory)", who, d->D);
-  SGV3D_REQUIRE(d->C <= 256, "%s: C=%d > 256 unsupported by the fused path", who, d->C);
-  SGV3D_REQUIRE((long long)d->X * d->Y <= (long long)kMaxTiles * 64,
-                "%s: X*Y exceeds %d voxels per frame", who, kMaxTiles * 64);
-  SGV3D_REQUIRE(d->arith >= SGV3D_ARITH_SEQ && d->arith <= SGV3D_ARITH_PAIR, "%s: bad arith", who);
-  SGV3D_REQUIRE(d->ctx_dtype == SGV3D_DTYPE_F32 || d->ctx_dtype == SGV3D_DTYPE_BF16, "%s: bad ctx_dtype", who);
-  SGV3D_REQUIRE(d->height_is_logits == 0 || d->height_is_logits == 1, "%s: bad height_is_logits", who);
-  SGV3D_REQUIRE(d->height_batch_stride >= 0 && d->ctx_batch_stride >= 0 && d->grad_height_batch_stride >= 0 &&
-                    d->grad_ctx_batch_stride >= 0, "%s: negative batch stride", who);
-  const long long slots = (long long)d->Nc * ceil_div(d->fH * d->fW, kChunk) * kChunk * d->D;
-  SGV3D_REQUIRE(slots < (1ll << 31), "%s: more than 2^31 height-bin slots per frame", who);
-  // a frame's channels-last context rows are addressed by 32-bit byte offsets, pixel rows by 26 bits
-  SGV3D_REQUIRE((long long)d->Nc * d->fH * d->fW < (1ll << 26) &&
-                    (long long)d->Nc * d->fH * d->fW * 4 * 256 < (1ll << 32),
-                "%s: more than 2^22 pixels per frame", who);
-  return SGV3D_OK;
-}
-
 int check_ws(const Workspace &w, void *ws, size_t bytes, const char *who) {
   if (!ws || bytes < w.bytes) {
     set_error("%s: workspace %zu < required %zu bytes", who, bytes, w.bytes);
     return SGV3D_ERR_WORKSPACE_TOO_SMALL;
   }
-  return SGV3D_OK;
-}
-
-// 16-byte cp.async is legal when every (camera, bin, chunk) row start is 16-byte aligned
-bool columns_vec16(const float *base, long long batch_stride, int P) {
-  return (reinterpret_cast<uintptr_t>(base) % 16 == 0) && (batch_stride % 4 == 0) && (P % 4 == 0);
-}
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-  if (bytes > 40 * 1024)  // dynamic + static shared memory beyond 48 KB needs the opt-in
-    SGV3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return SGV3D_OK;
 }
 
@@ -1840,6 +1716,31 @@ int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, cons
              : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s);
 }
 
+// Which pipeline serves this descriptor: desc->reserved[0] = 0 (auto: the pixel-block pipeline of
+// lift_splat_block.cu when it supports the shape), 1 (voxel-tile pipeline of this file), 2 (pixel-block, required).
+bool use_block(const sgv3d_lift_splat_desc *desc, const Dims &m) {
+  if (desc->reserved[0] == 1) return false;
+  return block::supported(m);
+}
+// the pixel-block pipeline's workspace follows the voxel-tile pipeline's
+void *block_ws(void *workspace, const Dims &m, int ctx_dtype) {
+  return static_cast<char *>(workspace) + carve(nullptr, m, ctx_dtype).bytes;
+}
+int check_pipeline(const sgv3d_lift_splat_desc *desc, const Dims &m, const char *who) {
+  SGV3D_REQUIRE(desc->reserved[0] >= 0 && desc->reserved[0] <= 2, "%s: bad pipeline selector %d", who, desc->reserved[0]);
+  SGV3D_REQUIRE(desc->reserved[0] != 2 || block::supported(m), "%s: the pixel-block pipeline does not support this shape", who);
+  return SGV3D_OK;
+}
+geom::Grid make_grid(const Dims &m, const float *lower3, const float *size3) {
+  geom::Grid grid;
+  for (int k = 0; k < 3; ++k) { grid.lower[k] = lower3[k]; grid.size[k] = size3[k]; }
+  grid.X = m.X; grid.Y = m.Y; grid.Z = m.Z;
+  geom::z_thresholds(grid.size[2], m.Z, &grid.zt_lo, &grid.zt_hi);
+  grid.rcp_size[0] = 1.0f / grid.size[0];  // IEEE single division on the host: correctly rounded
+  grid.rcp_size[1] = 1.0f / grid.size[1];
+  return grid;
+}
+
 }  // namespace
 }  // namespace sgv3d
 
@@ -1848,7 +1749,7 @@ using namespace sgv3d;
 extern "C" size_t sgv3d_lift_splat_workspace_bytes(const sgv3d_lift_splat_desc *desc) {
   if (validate(desc, "lift_splat_workspace_bytes") != SGV3D_OK || desc->B == 0) return 0;
   const Dims m = make_dims(desc);
-  return carve(nullptr, m, desc->ctx_dtype).bytes;
+  return carve(nullptr, m, desc->ctx_dtype).bytes + (block::supported(m) ? block::workspace_bytes(m) : 0);
 }
 
 extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const float *u_tab,
@@ -1863,16 +1764,16 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
                 "lift_splat_plan: null pointer");
   SGV3D_REQUIRE(size3[0] > 0.f && size3[1] > 0.f && size3[2] > 0.f, "lift_splat_plan: voxel size must be > 0");
   const Dims m = make_dims(desc);
-  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_pipeline(desc, m, "lift_splat_plan")) return rc;
+  Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (block::supported(m)) w.bytes += block::workspace_bytes(m);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
-  geom::Grid grid;
-  for (int k = 0; k < 3; ++k) { grid.lower[k] = lower3[k]; grid.size[k] = size3[k]; }
-  grid.X = m.X; grid.Y = m.Y; grid.Z = m.Z;
-  geom::z_thresholds(grid.size[2], m.Z, &grid.zt_lo, &grid.zt_hi);
-  grid.rcp_size[0] = 1.0f / grid.size[0];  // IEEE single division on the host: correctly rounded
-  grid.rcp_size[1] = 1.0f / grid.size[1];
+  const geom::Grid grid = make_grid(m, lower3, size3);
+  if (use_block(desc, m))
+    return block::plan(m, desc->arith, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda, ref_heights, grid,
+                       block_ws(workspace, m, desc->ctx_dtype), s);
 
   dim3 gc(m.nchunks, m.B);
   const int gen_grid = std::min(m.nchunks * m.B, 5 * kNumSMs);  // 5 CTAs of the general kernel fit on an SM
@@ -1921,8 +1822,12 @@ extern "C" int sgv3d_lift_splat_forward(const sgv3d_lift_splat_desc *desc, const
   const Dims m = make_dims(desc);
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward")) return rc;
+  if (int rc = check_pipeline(desc, m, "lift_splat_forward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
+  if (use_block(desc, m))
+    return block::forward(m, desc->ctx_dtype, height, context, nullptr, 0, 0, 0.0f, bev,
+                          block_ws(workspace, m, desc->ctx_dtype), s);
   if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, true, s)) return rc;
   if (desc->ctx_dtype == SGV3D_DTYPE_BF16) return launch_reduce<__nv_bfloat16>(m, w, bev, s);
   return launch_reduce<float>(m, w, bev, s);
@@ -1945,8 +1850,13 @@ extern "C" int sgv3d_lift_splat_forward_bsm(const sgv3d_lift_splat_desc *desc, c
   if (!desc->ctx_batch_stride) m.cs = (long long)(m.C - semantic_channels) * m.P;
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_forward_bsm")) return rc;
+  if (int rc = check_pipeline(desc, m, "lift_splat_forward_bsm")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
+  if (use_block(desc, m))
+    return block::forward(m, desc->ctx_dtype, height, context, semantic_logits, semantic_channels,
+                          semantic_batch_stride ? semantic_batch_stride : (long long)semantic_channels * m.P,
+                          background_threshold, bev, block_ws(workspace, m, desc->ctx_dtype), s);
   BsmAssembly bsm;
   bsm.sem = semantic_logits;
   bsm.sem_stride = semantic_batch_stride ? semantic_batch_stride : (long long)semantic_channels * m.P;
@@ -1967,8 +1877,12 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
   const Dims m = make_dims(desc);
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_backward")) return rc;
+  if (int rc = check_pipeline(desc, m, "lift_splat_backward")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   prof_begin(s);
+  if (use_block(desc, m))
+    return block::backward(m, desc->ctx_dtype, grad_bev, height, context, grad_height, grad_context,
+                           block_ws(workspace, m, desc->ctx_dtype), s);
   const int gpad = m.Cpad;  // gradient rows share the context rows' (permuted) channel layout
   if (m.C <= 96) {
     // fused path: 4-lane gradient rows of its own (16 * ceil(C / 16) floats <= Cpad, so gT is large enough)
@@ -2009,8 +1923,11 @@ extern "C" int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, i
   const Dims m = make_dims(desc);
   const Workspace w = carve(workspace, m, desc->ctx_dtype);
   if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_plan_expand")) return rc;
+  if (int rc = check_pipeline(desc, m, "lift_splat_plan_expand")) return rc;
   dim3 gc(m.nchunks, m.B);
   prof_begin(static_cast<cudaStream_t>(stream));
+  if (use_block(desc, m))
+    return block::plan_expand(m, vox_out, block_ws(workspace, m, desc->ctx_dtype), static_cast<cudaStream_t>(stream));
   ls_expand_kernel<2><<<gc, kChunk, 0, static_cast<cudaStream_t>(stream)>>>(
       m, nullptr, 0, w.run_cnt, w.run_d, w.run_vox, nullptr, nullptr, nullptr, vox_out);
   SGV3D_CHECK_LAUNCH("ls_expand_kernel(vox)");

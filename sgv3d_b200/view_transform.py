@@ -24,7 +24,7 @@ from torch.autograd import Function
 from . import _native as N
 
 __all__ = ["camera_matrices", "inverse4x4", "geometry_indices", "LiftSplatPlan", "lift_splat", "LiftSplat", "LiftSplatGraph",
-           "build_frustum", "default_arith"]
+           "build_frustum", "default_arith", "set_default_pipeline", "PIPELINE_AUTO", "PIPELINE_TILE", "PIPELINE_BLOCK"]
 
 _DEFAULT_ARITH = N.ARITH_PAIR
 
@@ -40,6 +40,18 @@ def set_default_arith(arith: int) -> None:
     global _DEFAULT_ARITH
     assert arith in (N.ARITH_SEQ, N.ARITH_FMA, N.ARITH_PAIR)
     _DEFAULT_ARITH = arith
+
+
+PIPELINE_AUTO, PIPELINE_TILE, PIPELINE_BLOCK = 0, 1, 2
+_DEFAULT_PIPELINE = PIPELINE_AUTO
+
+
+def set_default_pipeline(pipeline: int) -> None:
+    """Which kernels serve new plans: AUTO (the pixel-block pipeline whenever it supports the shape -- rows of up to
+    96 channels, D <= 255 -- else the voxel-tile pipeline), TILE or BLOCK (forced; tests compare the two)."""
+    global _DEFAULT_PIPELINE
+    assert pipeline in (PIPELINE_AUTO, PIPELINE_TILE, PIPELINE_BLOCK)
+    _DEFAULT_PIPELINE = pipeline
 
 
 def build_frustum(final_dim: Sequence[int], downsample_factor: int, d_bound: Sequence[float]) -> torch.Tensor:
@@ -267,7 +279,7 @@ class LiftSplatPlan:
     def __init__(self, frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
                  bda_mat, voxel_coord, voxel_size, voxel_num: Sequence[int], channels: int,
                  ctx_dtype: torch.dtype = torch.float32, arith: Optional[int] = None,
-                 grid_const: Optional[_GridConst] = None):
+                 grid_const: Optional[_GridConst] = None, pipeline: Optional[int] = None):
         g = _Geometry(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
                       bda_mat, voxel_coord, voxel_size, grid_const)
         self.geometry = g
@@ -279,6 +291,7 @@ class LiftSplatPlan:
         self.desc = N.LiftSplatDesc(B=g.B, Nc=g.Nc, D=g.D, fH=g.fH, fW=g.fW, C=int(channels), X=nx, Y=ny, Z=nz,
                                     arith=default_arith() if arith is None else arith,
                                     ctx_dtype=N.DTYPE_BF16 if ctx_dtype == torch.bfloat16 else N.DTYPE_F32)
+        self.desc.reserved[0] = _DEFAULT_PIPELINE if pipeline is None else pipeline
         L = N.lib()
         self.ws_bytes = L.sgv3d_lift_splat_workspace_bytes(self.desc)
         if g.B > 0 and self.ws_bytes == 0:

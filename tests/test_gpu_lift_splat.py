@@ -11,6 +11,16 @@ from tests.helpers import frustum_axes, kept_mask_np, oracle_frustum
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["tile", "auto"])
+def pipeline(request):
+    """Every test of this file runs on both kernel pipelines: "tile" = voxel-tile (global sort by voxel + row gathers),
+    "auto" = the pixel-block pipeline wherever it supports the shape (C <= 96, D <= 255), else voxel-tile."""
+    from sgv3d_b200 import view_transform as VT
+    VT.set_default_pipeline(VT.PIPELINE_TILE if request.param == "tile" else VT.PIPELINE_AUTO)
+    yield request.param
+    VT.set_default_pipeline(VT.PIPELINE_AUTO)
+
 RTOL, ATOL = 1e-5, 1e-5           # fp32 tolerance stated by BASELINE.json:north_star
 RTOL_BF16, ATOL_BF16 = 1e-2, 1e-3  # bf16-context variant vs the fp32 oracle fed the same bf16-rounded inputs
 
@@ -38,7 +48,11 @@ def _setup(shape_name, batch, num_cams, seed, bda, arith=0, ctx_dtype=torch.floa
 
 
 CASES = [("tiny", 2, 2, None), ("small", 3, 1, "random"), ("dair_r50", 2, 1, "identity"),
-         ("rope3d_r50", 1, 1, "identity"), ("sgv3d_bsm_r50", 1, 1, "identity"), ("dair_r50_256", 1, 1, "identity")]
+         ("rope3d_r50", 1, 1, "identity"), ("sgv3d_bsm_r50", 1, 1, "identity"), ("dair_r50_256", 1, 1, "identity"),
+         # D = 180 / 256 x 256 and 352 x 352 grids (exps/bevheight/rope3d/bev_height_lss_r101_864_1536_256x256.py:45-54,
+         # exps/sgv3d/bsm_bev_height_lss_r101_864_1536_256x256.py:43-46, ...r101_140.8...:45-54), random BDA, 2 cameras
+         ("rope3d_r101_256", 1, 1, "identity"), ("sgv3d_bsm_r101", 1, 1, "identity"), ("rope3d_r101_140", 1, 1, "random"),
+         ("rope3d_native", 1, 2, "random")]
 
 
 @pytest.mark.parametrize("shape_name,batch,num_cams,bda", CASES)
@@ -395,3 +409,166 @@ def test_camera_prep_kernel_is_bit_identical_to_torch(batch, num_cams):
     for got in (_camera_prep(s2e, s2v, k, ida), camera_matrices(s2e, s2v, k, ida)):
         for w, g in zip(want, got):
             assert torch.equal(w.view(torch.int32), g.contiguous().view(torch.int32))
+
+
+# ---- fused-path edge cases: through plan -> forward -> backward, against the oracle ----------------
+def _plan_from(shape, mats, channels=None, ctx_dtype=torch.float32, arith=2):
+    from sgv3d_b200.view_transform import LiftSplatPlan
+    fr = oracle_frustum(shape)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    dev = {k: (v.cuda() if v is not None else None) for k, v in mats.items()}
+    plan = LiftSplatPlan(fr, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"],
+                         dev["reference_heights"], dev["bda"], vc, vs, shape.grid, channels or shape.channels,
+                         ctx_dtype=ctx_dtype, arith=arith)
+    return plan, fr, vs, vc, dev
+
+
+def _indices_like_the_gpu(shape, fr, vs, vc, dev, arith=2):
+    """voxel indices of the standalone geometry kernel (always the full chain; itself pinned against the C oracle
+    and the reference port by tests/test_gpu_geometry.py), as numpy"""
+    from sgv3d_b200.view_transform import geometry_indices
+    return geometry_indices(fr, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"],
+                            dev["reference_heights"], dev["bda"], vc, vs, arith=arith).cpu().numpy()
+
+
+def test_fused_path_nan_and_inf_rays():
+    """A camera whose virtual-camera ray has pv.y == 0 for a whole image row (height / 0 = +-Inf, 0 / 0 = NaN;
+    lss_fpn.py:363) and a BDA that spreads the NaN (lss_fpn.py:394-398): on the GPU `.int()` maps NaN to 0, so such
+    points are KEPT in voxel (0, 0, 0).  Plan, forward and backward must agree with the oracle fed the same indices."""
+    shape = get_shape("small")
+    B = 2
+    mats = make_mats(shape, B, 1, seed=51, bda="random")
+    # frame 0: sensor2virtual @ K^-1 with a zero second row => pv.y == 0 everywhere => ratio = +-Inf / NaN
+    mats["sensor2virtual"][0, 0, 1, :] = 0.0
+    # frame 1: reference height NaN => every point NaN
+    mats["reference_heights"][1, 0] = float("nan")
+    plan, fr, vs, vc, dev = _plan_from(shape, mats)
+    idx = _indices_like_the_gpu(shape, fr, vs, vc, dev)
+    X, Y, Z = shape.grid
+    kept = kept_mask_np(idx, shape.grid)
+    want = np.where(kept, idx[..., 1] * X + idx[..., 0], -1).astype(np.int32)
+    got = plan.expand().cpu().numpy()
+    assert int((got != want).sum()) == 0
+    assert kept[1].all() and (want[1] == 0).all()          # NaN rays: kept, voxel 0
+    logits, ctx = make_activations(shape, B, 1, seed=51)
+    height = logits.softmax(1)
+    bev = plan.forward(height.cuda(), ctx.cuda())
+    want_bev = CO.lift_splat_forward64(idx, height.numpy(), ctx.numpy(), X, Y, Z)
+    np.testing.assert_allclose(bev.cpu().numpy(), want_bev, rtol=RTOL, atol=ATOL)
+    gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(8))
+    g_h, g_c = plan.backward(gb.cuda(), height.cuda(), ctx.cuda())
+    gh64, gc64 = CO.lift_splat_backward64(idx, height.numpy(), ctx.numpy(), gb.numpy(), X, Y, Z)
+    np.testing.assert_allclose(g_h.cpu().numpy(), gh64, rtol=RTOL, atol=ATOL * 10)
+    np.testing.assert_allclose(g_c.cpu().numpy(), gc64, rtol=RTOL, atol=ATOL)
+
+
+def test_fused_path_frame_with_every_point_dropped_and_empty_batch():
+    """Frame 1 looks away from the grid (camera yawed by 180 degrees): no point is kept, its BEV map must be all
+    zeros and its gradients zero; frame 0 is a normal frame.  Then B = 0: empty outputs, no launch failure."""
+    shape = get_shape("small")
+    B = 2
+    mats = make_mats(shape, B, 1, seed=52, bda="identity")
+    flip = torch.diag(torch.tensor([-1.0, -1.0, 1.0, 1.0]))
+    mats["sensor2ego"][1, 0] = flip @ mats["sensor2ego"][1, 0]
+    plan, fr, vs, vc, dev = _plan_from(shape, mats)
+    idx = _indices_like_the_gpu(shape, fr, vs, vc, dev)
+    X, Y, Z = shape.grid
+    kept = kept_mask_np(idx, shape.grid)
+    assert kept[0].any() and not kept[1].any()
+    got = plan.expand().cpu().numpy()
+    assert (got[1] == -1).all()
+    logits, ctx = make_activations(shape, B, 1, seed=52)
+    height = logits.softmax(1)
+    bev = plan.forward(height.cuda(), ctx.cuda())
+    want_bev = CO.lift_splat_forward64(idx, height.numpy(), ctx.numpy(), X, Y, Z)
+    np.testing.assert_allclose(bev.cpu().numpy(), want_bev, rtol=RTOL, atol=ATOL)
+    assert float(bev[1].abs().max()) == 0.0
+    gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(9))
+    g_h, g_c = plan.backward(gb.cuda(), height.cuda(), ctx.cuda())
+    assert float(g_h[1].abs().max()) == 0.0 and float(g_c[1].abs().max()) == 0.0
+    gh64, gc64 = CO.lift_splat_backward64(idx, height.numpy(), ctx.numpy(), gb.numpy(), X, Y, Z)
+    np.testing.assert_allclose(g_h.cpu().numpy(), gh64, rtol=RTOL, atol=ATOL * 10)
+    np.testing.assert_allclose(g_c.cpu().numpy(), gc64, rtol=RTOL, atol=ATOL)
+    # B = 0
+    empty = {k: (v[:0] if v is not None else None) for k, v in mats.items()}
+    plan0, *_ = _plan_from(shape, empty)
+    h0 = torch.zeros(0, shape.D, shape.fH, shape.fW, device="cuda")
+    c0 = torch.zeros(0, shape.channels, shape.fH, shape.fW, device="cuda")
+    bev0 = plan0.forward(h0, c0)
+    assert tuple(bev0.shape) == (0, shape.channels, Y, X)
+    gh0, gc0 = plan0.backward(torch.zeros(0, shape.channels, Y, X, device="cuda"), h0, c0)
+    assert gh0.numel() == 0 and gc0.numel() == 0
+    assert plan0.expand().numel() == 0
+
+
+def test_matches_reference_port_run_on_the_gpu():
+    """The torch port of _forward_single_sweep (lss_fpn.py:462-495) executed ON THE GPU -- the device the reference
+    runs on -- against the module: voxel indices bit-exact (0 flips), BEV map and gradients within tolerance."""
+    from sgv3d_b200 import LiftSplat
+    shape = get_shape("small")
+    B = 3
+    mats = make_mats(shape, B, 1, seed=44, bda="random")
+    logits, ctx = make_activations(shape, B, 1, seed=44)
+    fr = oracle_frustum(shape)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    gb = torch.randn(B, shape.channels, shape.grid[1], shape.grid[0], generator=torch.Generator().manual_seed(3))
+    cm = {k: (v.cuda() if v is not None else None) for k, v in mats.items()}
+    bev_o, gl_o, gc_o = O.lift_splat_forward_backward(logits.cuda(), ctx.cuda(), fr.cuda(), cm, vc.cuda(), vs.cuda(),
+                                                      vn, gb.cuda())
+    idx_o = O.quantize(O.geometry_matmul(fr.cuda(), cm["sensor2ego"], cm["sensor2virtual"], cm["intrin"], cm["ida"],
+                                         cm["reference_heights"], cm["bda"]), vc.cuda(), vs.cuda())
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                    shape.downsample, shape.channels).cuda()
+    md = {"sensor2ego_mats": cm["sensor2ego"].unsqueeze(1), "sensor2virtual_mats": cm["sensor2virtual"].unsqueeze(1),
+          "intrin_mats": cm["intrin"].unsqueeze(1), "ida_mats": cm["ida"].unsqueeze(1),
+          "reference_heights": cm["reference_heights"].unsqueeze(1), "bda_mat": cm["bda"]}
+    idx_k = mod.get_geometry_indices(md["sensor2ego_mats"][:, 0], md["sensor2virtual_mats"][:, 0], md["intrin_mats"][:, 0],
+                                     md["ida_mats"][:, 0], md["reference_heights"][:, 0], md["bda_mat"])
+    assert int((idx_k != idx_o).sum()) == 0
+    hf = torch.cat((logits, ctx), 1).cuda().requires_grad_(True)
+    bev = mod.forward_single_sweep(hf, md)
+    bev.backward(gb.cuda())
+    torch.testing.assert_close(bev, bev_o, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(hf.grad[:, shape.D:], gc_o, rtol=RTOL, atol=ATOL)
+    # d/d logits: a sum of D products of O(sqrt(C)) terms through the softmax Jacobian -- rtol 1e-4 (stated in DESIGN.md 2)
+    torch.testing.assert_close(hf.grad[:, :shape.D], gl_o, rtol=1e-4, atol=ATOL)
+
+
+def test_bsm_gradients_vs_oracle():
+    """BSMLSSFPN call site under autograd (bsm_lss_fpn.py:523-541): gradients w.r.t. the height logits, the semantic
+    logits and the context against torch autograd over the port (O.bsm_context + O.lift + index_add_), fp64."""
+    from sgv3d_b200 import LiftSplat
+    shape = get_shape("small")
+    B = 2
+    mats = make_mats(shape, B, 1, seed=45, bda="identity")
+    g = torch.Generator().manual_seed(12)
+    fh, fw = shape.fH * 2, shape.fW * 2
+    hl = torch.randn(B, shape.D, fh, fw, generator=g)
+    sl = torch.randn(B, 7, fh, fw, generator=g) * 1.5
+    sl[:, 0] += 1.0
+    cx = torch.randn(B, 80, fh, fw, generator=g)
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                    shape.downsample, 87, is_bsm=True).cuda()
+    md = {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).cuda(), "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).cuda(),
+          "intrin_mats": mats["intrin"].unsqueeze(1).cuda(), "ida_mats": mats["ida"].unsqueeze(1).cuda(),
+          "reference_heights": mats["reference_heights"].unsqueeze(1).cuda(), "bda_mat": mats["bda"].cuda()}
+    a = [t.clone().cuda().requires_grad_(True) for t in (hl, sl, cx)]
+    bev = mod.forward_single_sweep_bsm(a[0], a[1], a[2], md)
+    gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(13))
+    bev.backward(gb.cuda())
+    # oracle: same indices (module's geometry kernel), fp64 autograd over the port
+    idx = mod.get_geometry_indices(md["sensor2ego_mats"][:, 0], md["sensor2virtual_mats"][:, 0], md["intrin_mats"][:, 0],
+                                   md["ida_mats"][:, 0], md["reference_heights"][:, 0], md["bda_mat"]).cpu()
+    o = [t.clone().double().requires_grad_(True) for t in (hl, sl, cx)]
+    feat = O.bsm_context(o[2], o[1])
+    # the mask is decided in fp32 by the reference; reuse the fp32 decision so that fp64 does not flip a pixel
+    mask32 = (sl.softmax(1)[:, 0:1] > 0.45)
+    feat = torch.cat((o[2], o[1].softmax(1)), 1) * (1 - mask32.int())
+    lifted = O.lift(o[0].softmax(1), feat).reshape(B, 1, 87, shape.D, fh, fw).permute(0, 1, 3, 4, 5, 2)
+    bev_o, _ = O.voxel_pooling_forward(idx, lifted.contiguous(), list(shape.grid))
+    bev_o = bev_o.contiguous()
+    bev_o.backward(gb.double())
+    torch.testing.assert_close(bev.detach().cpu().double(), bev_o.detach(), rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(a[2].grad.cpu().double(), o[2].grad, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(a[1].grad.cpu().double(), o[1].grad, rtol=1e-4, atol=ATOL)
+    torch.testing.assert_close(a[0].grad.cpu().double(), o[0].grad, rtol=1e-4, atol=ATOL)

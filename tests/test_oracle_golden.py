@@ -110,3 +110,18 @@ def test_quantize_edge_semantics():
                             [2147483647, -2147483648, 0], [1, 1, 1]]
     vc = lower + size / np.float32(2.0)
     assert np.array_equal(O.quantize_np(pts, vc, size), idx)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_product_build_frustum_matches_the_reference_buffer(name):
+    """sgv3d_b200.build_frustum (the PRODUCT's copy of LSSFPN.create_frustum, lss_fpn.py:325-348) against the frustum
+    buffer the reference's own code produced (tests/golden/make_golden.py): bit-exact u / v / z axes."""
+    from sgv3d_b200.view_transform import build_frustum
+    g = load_golden(name)
+    shape = g["shape"]
+    fr = build_frustum(shape.final_dim, shape.downsample, shape.d_bound)
+    u, v, z = (t.numpy() for t in frustum_axes(fr))
+    for got, key in ((u, "frustum_u"), (v, "frustum_v"), (z, "frustum_z")):
+        want = g[key]
+        assert got.shape == want.shape and (got.view(np.int32) == want.view(np.int32)).all(), key
+    assert float(fr[..., 3].min()) == 1.0 == float(fr[..., 3].max())

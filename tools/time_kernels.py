@@ -8,7 +8,10 @@ from sgv3d_b200.synthetic import make_activations, make_mats  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="dair_r50"); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--iters", type=int, default=20); ap.add_argument("--bf16", action="store_true")
+ap.add_argument("--pipeline", default="auto", choices=["auto", "tile", "block"])
 a = ap.parse_args()
+from sgv3d_b200 import view_transform as VT  # noqa: E402
+VT.set_default_pipeline({"auto": VT.PIPELINE_AUTO, "tile": VT.PIPELINE_TILE, "block": VT.PIPELINE_BLOCK}[a.pipeline])
 s = get_shape(a.shape); dev = torch.device("cuda", 0)
 mod = LiftSplat(s.x_bound, s.y_bound, s.z_bound, s.d_bound, s.final_dim, s.downsample, s.channels).to(dev)
 mats = make_mats(s, a.batch, 1, seed=5, bda="identity")
@@ -31,4 +34,4 @@ for phase, fn in (("plan", plan.rebuild), ("forward", lambda: plan.forward(logit
     torch.cuda.synchronize()
     prof = N.profile_report(); N.profile_enable(False)
     tot = sum(t for _, t in prof.values()) / a.iters
-    print(f"{phase}: {1e3 * tot:.1f} us  " + "  ".join(f"{k}={1e3 * t / n:.1f}" for k, (n, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])))
+    print(f"[{a.shape} B={a.batch} {a.pipeline}] {phase}: {1e3 * tot:.1f} us  " + "  ".join(f"{k}={1e3 * t / n:.1f}" for k, (n, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])))
