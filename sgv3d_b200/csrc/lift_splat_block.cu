@@ -893,7 +893,8 @@ bp_expand_kernel(BDims m, const int *__restrict__ cnt_in, const int *__restrict_
   for (; dc < m.D; ++dc) out[(size_t)dc * m.P] = -1;
 }
 
-size_t smem_budget() { return 113 * 1024; }   // two CTAs per SM (227 KB usable)
+// two CTAs per SM: 228 KB per SM, 1 KB of it reserved per CTA, plus the kernels' few static words
+size_t smem_budget() { return 111 * 1024; }
 
 int forward_cap(const BDims &m, int Cs) {
   const size_t fixed = sizeof(float) * ((size_t)m.D * kBP + (size_t)kBP * m.Cpad + (size_t)Cs * kBP);
