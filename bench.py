@@ -46,8 +46,8 @@ def _peaks():
 def _ncu_traffic(kernels, shape_name, frames):
     """DRAM bytes (read + write) of one step from the committed ``ncu --set full`` capture
     (profiles/traffic_r01.json, written by tools/ncu_traffic.py; per launch at the capture's batch), summed over the kernels of this step."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if not os.path.exists(p):
+    p = _traffic_file()
+    if p is None:
         return None
     t = json.load(open(p))
     if t.get("shape") != shape_name or t.get("frames_per_launch") != frames:
@@ -58,6 +58,44 @@ def _ncu_traffic(kernels, shape_name, frames):
             return None
         tot += t["dram_bytes_per_launch"][base]
     return tot
+
+
+def _traffic_file():
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def _pct(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    k = (len(xs) - 1) * q
+    lo, hi = int(k), min(int(k) + 1, len(xs) - 1)
+    return xs[lo] + (xs[hi] - xs[lo]) * (k - lo)
+
+
+def _windows(fn, steps, repeats, sync):
+    """`repeats` back-to-back windows of `steps` calls, each timed with CUDA events on the current stream;
+    returns ms per step of every window."""
+    out = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(repeats):
+        sync()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync()
+        out.append(e0.elapsed_time(e1) / steps)
+    return out
+
+
+def _stats(xs):
+    return {"n_windows": len(xs), "ms_per_step_median": statistics.median(xs), "ms_per_step_p10": _pct(xs, 0.1),
+            "ms_per_step_p90": _pct(xs, 0.9), "ms_per_step_min": min(xs), "ms_per_step_max": max(xs)}
 
 
 def _mats_dict(mats, device):
@@ -117,6 +155,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _prep_path(dev, B):
+    """which implementation of the per-camera 4x4 prep (lss_fpn.py:361,367,392) served this run"""
+    from sgv3d_b200 import view_transform as VT
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ok = VT._CAMERA_PREP_OK.get((idx, (B, 1, 4, 4)))
+    if ok:
+        return "sgv3d_camera_prep (one kernel, verified bit-identical to torch at first use)"
+    if VT._INVERSE_KERNEL_OK.get(idx):
+        return "sgv3d_inverse4x4 + torch matmul (camera_prep differed from torch on this installation)"
+    return "torch inverse / matmul (library prep kernels differed from torch on this installation)"
+
+
+def _pipeline_name(plan):
+    sel = int(plan.desc.reserved[0])
+    from sgv3d_b200 import _native as N
+    blk = bool(N.lib().sgv3d_lift_splat_uses_block_pipeline(plan.desc))
+    return ("pixel-block" if blk else "voxel-tile") + (" (auto)" if sel == 0 else " (forced)")
+
+
 def _dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -132,10 +189,14 @@ def cpu_reference_run(shape, frames: int, warmup: int, budget_s: float = 40.0):
     get_geometry materialises ~40 MB of intermediates per frame; batching frames does not help it).
     Returns (frames_per_s, frames_timed, cores, seconds)."""
     from oracle import lift_splat_oracle as O
+    from oracle import ref_cpu as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     fr = O.create_frustum(shape.final_dim, shape.downsample, shape.d_bound)
     vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    # the reference's own get_geometry / create_frustum (bytecode of the unmodified lss_fpn.py, oracle/_ref) when it
+    # was staged by `make -C oracle ref`; else the line-by-line port
+    ref_mod = R.make_module(shape) if R.available() else None
     # a few distinct inputs, rotated (generating them is not part of the timed path)
     nin = 4
     inputs = []
@@ -148,14 +209,22 @@ def cpu_reference_run(shape, frames: int, warmup: int, budget_s: float = 40.0):
     for i in range(warmup + frames):
         mats, logits, ctx = inputs[i % nin]
         t0 = time.perf_counter()
-        O.lift_splat_forward(logits, ctx, fr, mats, vc, vs, vn)
+        if ref_mod is not None:
+            R.forward(ref_mod, logits, ctx, mats)
+        else:
+            O.lift_splat_forward(logits, ctx, fr, mats, vc, vs, vn)
         dt = time.perf_counter() - t0
         if i >= warmup:
             total += dt
             n += 1
         if time.perf_counter() - t_begin > budget_s and n >= 2:
             break
-    return n / total, n, cores, total
+    return n / total, n, cores, total, ("reference" if ref_mod is not None else "port")
+
+
+_KIND_TEXT = {"reference": "the reference's own LSSFPN.get_geometry / create_frustum (unmodified lss_fpn.py, byte-compiled into "
+                           "oracle/_ref) + the lss_fpn.py:462-495 glue + torch-CPU index_add_ for the CUDA-only voxel_pooling op",
+              "port": "torch-CPU port of the reference path (oracle/lift_splat_oracle.py)"}
 
 
 def run_reference(args):
@@ -165,10 +234,10 @@ def run_reference(args):
     shape = get_shape(args.shape)
     B, K, W = args.batch, args.steps, max(args.warmup, 1)
     # one step = the same B frames per step as our arm; the run is capped at ~2.5 minutes of CPU work
-    fps, n, cores, total = cpu_reference_run(shape, B * K, B * W if B * W < 64 else 64, budget_s=150.0)
+    fps, n, cores, total, kind = cpu_reference_run(shape, B * K, B * W if B * W < 64 else 64, budget_s=150.0)
     steps_done = n / B
-    sample = (f"{n} frame(s) of {shape.name} ({steps_done:.2f} step(s) of {B} frames), forward only, torch-CPU port of the "
-              f"reference path (oracle/lift_splat_oracle.py), {total:.1f} s on {cores} host threads")
+    sample = (f"{n} frame(s) of {shape.name} ({steps_done:.2f} step(s) of {B} frames), forward only, {_KIND_TEXT[kind]}, "
+              f"{total:.1f} s on {cores} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 * B / fps, "higher_is_better": True,
@@ -176,7 +245,7 @@ def run_reference(args):
         "config": {"workload": f"{shape.name} lift-splat forward (softmax + get_geometry + lift + index_add_ pooling) on "
                                f"the host CPU, {B} frames per step", "frames_per_step_per_gpu": B, "shape": shape.name,
                    "D": shape.D, "fH": shape.fH, "fW": shape.fW, "C": shape.channels, "grid": list(shape.grid)},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -285,6 +354,32 @@ def run_ours(args):
         torch.cuda.synchronize()
     clocks = sampler.stop()
     clocks["span"] = "timed region + >= 0.4 s of the same step loop (nvidia-smi -lms 20)"
+    # ---- >= 100 iterations, median + p10 / p90: more windows of the same K steps (the contract window
+    # above stays the one `value` is computed from)
+    R = max(1, args.repeats)
+    fwd_windows = [ms / K] + _windows(step, K, R - 1, barrier)
+
+    # ---- training step: plan + fused forward + fused backward (north star: fwd+bwd roofline), raw plan API on the
+    # head's logits, distinct calibration per frame, rotating input sets, graph-free (3 library calls per step)
+    from sgv3d_b200.view_transform import LiftSplatPlan  # noqa: F401
+    D_, C_ = shape.D, shape.channels
+    train_sets = []
+    for hf, md, _ in sets:
+        plan = mod.make_plan(md, 0, C_)
+        gb = torch.randn(B, C_, shape.grid[1], shape.grid[0], device=dev)
+        gout = torch.empty_like(hf)
+        train_sets.append((plan, hf, gb, gout))
+
+    def train_step(i):
+        plan, hf, gb, gout = train_sets[i % nsets]
+        plan.rebuild()
+        plan.forward(hf[:, :D_], hf[:, D_:D_ + C_], logits=True)
+        plan.backward(gb, hf[:, :D_], hf[:, D_:D_ + C_], logits=True, out_height=gout[:, :D_], out_context=gout[:, D_:D_ + C_])
+
+    for i in range(W):
+        train_step(i)
+    train_windows = _windows(train_step, K, R, barrier)
+
     ms_eager = None
     if not args.eager:
         for i in range(3):
@@ -343,9 +438,11 @@ def run_ours(args):
     # ---- max over ranks ---------------------------------------------------------------------------
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e] + fwd_windows + train_windows, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+        fwd_windows = [float(x) for x in t[2:2 + len(fwd_windows)]]
+        train_windows = [float(x) for x in t[2 + len(fwd_windows):]]
     frames_total = B * K * world
     value = frames_total / (ms * 1e-3)
     e2e_value = frames_total / (ms_e2e * 1e-3)
@@ -361,36 +458,42 @@ def run_ours(args):
         return
 
     peak, peak_src = _peaks()
-    alg_bytes = shape.fused_forward_bytes() * B           # 8.77 MB/frame at DAIR-R50
-    # the kernels of one step run as ONE CUDA-graph launch (two branches: context rows || 4x4 prep + plan, then
-    # weights + reduce); its duration is the device-timed step above (CUDA events, same stream), which also
-    # contains the dozen tiny torch launches of the reference's per-camera 4x4 products
+    fwd_bytes = shape.fused_forward_bytes() * B           # 8.77 MB/frame at DAIR-R50
+    train_bytes = fwd_bytes + shape.fused_backward_bytes() * B   # + 12.29 MB/frame = 21.06 MB/frame
+    # forward-only step: ONE CUDA-graph launch (4x4 prep + plan + forward); its duration is the device-timed contract
+    # window above.  Training step: plan + forward + backward, timed the same way (CUDA events on the launch stream).
     step_ms = ms / K
-    achieved = alg_bytes / (step_ms * 1e-3) / 1e9 if step_ms else 0.0
+    fwd_achieved = fwd_bytes / (step_ms * 1e-3) / 1e9 if step_ms else 0.0
+    train_ms = statistics.median(train_windows)
+    train_achieved = train_bytes / (train_ms * 1e-3) / 1e9
+    tf = _traffic_file()
+    # headline roofline: the north star's target quantity -- fused forward + backward of one step against the HBM
+    # roofline; the forward-only (inference) step is reported beside it
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "bound": "hbm", "achieved": train_achieved, "peak": peak, "unit": "GB/s", "frac": train_achieved / peak,
         "traffic": _ncu_traffic(list(kern.keys()), shape.name, B),
-        "kernel": "fused lift-splat forward = every kernel of one step (4x4 prep + plan + forward), one graph launch",
-        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": step_ms,
-        "kernel_sum_ms": lib_ms / K if K else 0.0, "peak_source": peak_src,
-        "frac_of_8TBs_nominal": achieved / 8000.0,
+        "traffic_source": ("committed ncu --set full capture %s (same shape and batch); not re-measured in this run"
+                           % os.path.relpath(tf, ROOT)) if tf else None,
+        "kernel": "fused lift-splat training step = plan + forward + backward kernels of one step (every kernel the "
+                  "library launches for %d frames)" % B,
+        "algorithmic_bytes_per_launch": train_bytes, "launch_ms": train_ms, "windows": _stats(train_windows),
+        "peak_source": peak_src, "frac_of_8TBs_nominal": train_achieved / 8000.0,
+        "forward_only": {
+            "kernel": "4x4 prep + plan + forward of one step, one CUDA-graph launch (the step `value` is computed from)",
+            "algorithmic_bytes_per_launch": fwd_bytes, "launch_ms": step_ms, "achieved": fwd_achieved,
+            "frac": fwd_achieved / peak, "windows": _stats(fwd_windows),
+            "kernel_sum_ms": lib_ms / K if K else 0.0},
         "dominant_kernel": dominant, "dominant_share": kern[dominant]["share"] if dominant else None,
         "kernels": kern,
     }
-    if "ls_reduce_kernel" in kern:
-        # the dominant kernel on its own: it must read every context row once and write the BEV map once
-        rb = (4 * shape.channels * shape.fH * shape.fW + 4 * shape.channels * shape.grid[0] * shape.grid[1]) * B
-        ra = rb / (kern["ls_reduce_kernel"]["avg_us"] * 1e-6) / 1e9
-        roofline["dominant_kernel_roofline"] = {
-            "kernel": "ls_reduce_kernel", "algorithmic_bytes_per_launch": rb, "launch_us": kern["ls_reduce_kernel"]["avg_us"],
-            "achieved": ra, "unit": "GB/s", "frac": ra / peak,
-            "note": "context rows read once + BEV written once; the event-timed launch includes ~5 us of launch gap"}
+    dom_fwd = max(((k, v) for k, v in kern.items()), key=lambda kv: kv[1]["avg_us"])[0] if kern else None
+    if dom_fwd is not None:
+        roofline["forward_only"]["dominant_kernel"] = dom_fwd
     cpu = None
     if world == 1:
-        fps, n, cores, total = cpu_reference_run(shape, 2000, 2, budget_s=12.0)
-        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} frame(s) of {shape.name}, forward only, torch-CPU port of the reference path "
-                         f"(oracle/lift_splat_oracle.py), {total:.1f} s"}
+        fps, n, cores, total, kind = cpu_reference_run(shape, 2000, 2, budget_s=12.0)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n} frame(s) of {shape.name}, forward only, {_KIND_TEXT[kind]}, {total:.1f} s"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -402,7 +505,11 @@ def run_ours(args):
                    "l2": f"working set per step ({(in_bytes + out_bytes) / 1e6:.0f} MB in+out, 2 rotating input "
                          f"sets) exceeds the 126 MB L2",
                    "sharding": "frames across ranks, no collective (replicas only)",
-                   "numa": "rank 0 bound to node %s" % numa_node if numa_node is not None else "not bound"},
+                   "numa": "rank 0 bound to node %s" % numa_node if numa_node is not None else "not bound",
+                   "camera_prep_path": _prep_path(dev, B),
+                   "pipeline": _pipeline_name(train_sets[0][0]),
+                   "timing": "W >= 3 warm-up steps; %d windows of %d steps each (CUDA events, barrier + synchronize on "
+                             "both sides); `value` from the first window, median / p10 / p90 in roofline.*.windows" % (R, K)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K,
@@ -488,6 +595,44 @@ def extra_measurements(args, shape, mod, sets, dev):
         sweep[str(nb)] = nb / (_time_loop(gb_, 10) * 1e-3)
         del gb_, hfb, mdb
     out["frames_per_s_by_batch"] = sweep
+    # the other BASELINE.json configs, short: forward step (plan rebuilt every step, CUDA-graph replay) and training
+    # step (plan + forward + backward) on the second mandatory shape, the Rope3D-shaped ones and the bf16-context
+    # training config (config 4: batch 8 per GPU)
+    from sgv3d_b200 import LiftSplat
+    shapes_out = {}
+    for nm, nb, dt in (("sgv3d_bsm_r50", 16, torch.float32), ("rope3d_r50", 32, torch.float32),
+                       ("rope3d_native", 32, torch.float32), ("dair_r50", 8, torch.bfloat16),
+                       ("sgv3d_bsm_r50", 8, torch.bfloat16)):
+        sh = get_shape(nm)
+        m2 = LiftSplat(sh.x_bound, sh.y_bound, sh.z_bound, sh.d_bound, sh.final_dim, sh.downsample, sh.channels).to(dev)
+        mats2 = make_mats(sh, nb, 1, seed=77, bda="identity")
+        md2 = _mats_dict(mats2, dev)
+        lg2, cx2 = make_activations(sh, nb, 1, seed=77, device=dev, generator_device=dev)
+        key = f"{nm}_b{nb}_{'bf16ctx' if dt == torch.bfloat16 else 'f32'}"
+        rec = {"frames": nb, "ctx_dtype": str(dt).split(".")[-1]}
+        ctx_b = 2 if dt == torch.bfloat16 else 4
+        fb2, bb2 = sh.fused_forward_bytes(ctx_b) * nb, sh.fused_backward_bytes(ctx_b) * nb
+        if dt == torch.float32:
+            hf2 = torch.cat((lg2, cx2), 1).contiguous()
+            g2 = LiftSplatGraph(m2, hf2, md2, warmup=1)
+            ms_f = _time_loop(g2, 10)
+            rec["forward_step"] = {"ms": ms_f, "frames_per_s": nb / (ms_f * 1e-3), "frac_of_measured_peak": fb2 / ms_f / 1e6 / peak}
+            del g2
+        plan2 = m2.make_plan(md2, 0, sh.channels, dt)
+        cxd = cx2.to(dt)
+        gb2 = torch.randn(nb, sh.channels, sh.grid[1], sh.grid[0], device=dev)
+
+        def tstep():
+            plan2.rebuild()
+            plan2.forward(lg2, cxd, logits=True)
+            plan2.backward(gb2, lg2, cxd, logits=True)
+        ms_t = _time_loop(tstep, 10)
+        rec["train_step"] = {"ms": ms_t, "frames_per_s": nb / (ms_t * 1e-3), "algorithmic_bytes": fb2 + bb2,
+                             "achieved_GBs": (fb2 + bb2) / ms_t / 1e6, "frac_of_measured_peak": (fb2 + bb2) / ms_t / 1e6 / peak}
+        rec["pipeline"] = _pipeline_name(plan2)
+        shapes_out[key] = rec
+        del plan2, m2
+    out["shapes"] = shapes_out
     # op-level drop-in (materialised frustum features are an API input there); the reference's own kernel,
     # recompiled for sm_100a, is timed on the same inputs by tests/bench_reference_kernel.py (test infrastructure)
     nb = min(B, 4)
@@ -513,6 +658,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--shape", default="dair_r50")
     ap.add_argument("--quick", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--repeats", type=int, default=5, help="timed windows of --steps steps each (median / p10 / p90)")
     ap.add_argument("--eager", action="store_true", help="time per-kernel launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

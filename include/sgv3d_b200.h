@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGV3D_ABI_VERSION 1
+#define SGV3D_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SGV3D_API __attribute__((visibility("default")))
@@ -159,8 +159,14 @@ typedef struct sgv3d_lift_splat_desc {
    * lss_fpn.py:461-466, without a copy.  Within one camera the [D|C][fH][fW] block is dense. */
   int64_t height_batch_stride, ctx_batch_stride;
   int64_t grad_height_batch_stride, grad_ctx_batch_stride;
+  /* reserved[0]: kernel pipeline -- 0 auto (the pixel-block pipeline, lift_splat_block.cu, whenever it supports the
+   * shape: C <= 96, D <= 255; else the voxel-tile pipeline, lift_splat.cu), 1 voxel-tile, 2 pixel-block (error if
+   * unsupported).  Must be the same for every call that shares a workspace.  reserved[1..3]: 0. */
   int32_t reserved[4];
 } sgv3d_lift_splat_desc;
+
+/* 1 when the calls for this descriptor run on the pixel-block pipeline, 0 for the voxel-tile pipeline. */
+SGV3D_API int sgv3d_lift_splat_uses_block_pipeline(const sgv3d_lift_splat_desc *desc);
 
 SGV3D_API size_t sgv3d_lift_splat_workspace_bytes(const sgv3d_lift_splat_desc *desc);
 

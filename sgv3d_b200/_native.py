@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsgv3d_b200.so")
 
 ARITH_SEQ, ARITH_FMA, ARITH_PAIR = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 #: every symbol ``include/sgv3d_b200.h`` declares (checked by tests/test_abi.py)
 SYMBOLS = (
@@ -24,6 +24,7 @@ SYMBOLS = (
     "sgv3d_geometry_quantize", "sgv3d_inverse4x4", "sgv3d_camera_prep",
     "sgv3d_lift_splat_workspace_bytes", "sgv3d_lift_splat_plan", "sgv3d_lift_splat_forward",
     "sgv3d_lift_splat_forward_bsm", "sgv3d_lift_splat_backward", "sgv3d_lift_splat_plan_expand",
+    "sgv3d_lift_splat_uses_block_pipeline",
     "sgv3d_profile_enable", "sgv3d_profile_report",
 )
 
@@ -74,6 +75,8 @@ def lib() -> ctypes.CDLL:
     P = ctypes.POINTER(LiftSplatDesc)
     L.sgv3d_lift_splat_workspace_bytes.restype = c_size_t
     L.sgv3d_lift_splat_workspace_bytes.argtypes = [P]
+    L.sgv3d_lift_splat_uses_block_pipeline.restype = c_int
+    L.sgv3d_lift_splat_uses_block_pipeline.argtypes = [P]
     L.sgv3d_lift_splat_plan.restype = c_int
     L.sgv3d_lift_splat_plan.argtypes = [P] + [c_void_p] * 11 + [c_size_t, c_void_p]
     L.sgv3d_lift_splat_forward.restype = c_int

@@ -348,16 +348,24 @@ struct LinearGuard {
 //                                      reference's fp32 chain may land on the other side) iff |e| > 0.5 - delta
 // Truncation toward zero (the reference's `.int()`) differs from floor only for Q in (-1, 0): that column is index
 // 0, so r = -1 is mapped to 0 when the index is formed (a spurious change at the 0 boundary then compares equal).
-// mode 0: the exact chain decides every bin; 1: linear form with per-bin guard; 2: every bin of the pixel is
-// provably dropped (a coordinate stays outside the grid by more than the guard band over the whole height range).
+// mode 0: the exact chain decides every bin; 1: linear form with per-bin guard, z provably inside the grid for the
+// whole pixel; 3: the same plus a per-bin z test (t_z = G_z - lower_z is linear in hgt as well: the bin is kept /
+// dropped by it unless t_z lies within its own guard band of a z threshold, where the exact chain decides --
+// Rope3D / SGV3D height bins reach 3.5 m, above the grid's z range [-5, 3]); 2: every bin of the pixel is provably
+// dropped (a coordinate stays outside the grid by more than the guard band over the whole height range).
 // ---------------------------------------------------------------------------------------------
 struct LinearWalk {
   float kx, cx, thx;  // q'_x = fma(hgt, kx, cx); unsafe iff |e_x| > thx
   float ky, cy, thy;
+  float kz, cz;            // t_z = fma(hgt, kz, cz)
+  float z_in_lo, z_in_hi;  // kept for sure:    z_in_lo < t_z < z_in_hi
+  float z_out_lo, z_out_hi;  // dropped for sure: t_z < z_out_lo or t_z > z_out_hi
   int mode;
 
-  __device__ __forceinline__ void init(float pv0, float pv1, float pv2, const float *me, float ref_h,
-                                       float p0z_lo, float p0z_hi, const Grid &g) {
+  // (not inlined: the fp64 set-up must run once per pixel -- inlined, the compiler re-materialises the constants
+  // inside the per-bin loop to save registers)
+  __device__ __noinline__ void init(float pv0, float pv1, float pv2, const float *me, float ref_h,
+                                    float p0z_lo, float p0z_hi, const Grid &g) {
     const double u32 = 1.9073486328125e-06;  // 32 * 2^-24
     const double rp = 1.0 / (double)pv1;
     const double h_lo = (double)ref_h - (double)p0z_hi, h_hi = (double)ref_h - (double)p0z_lo;
@@ -383,9 +391,9 @@ struct LinearWalk {
     // ranges of the real-valued coordinates over the pixel's height range (linear => the two ends decide)
     const double qxa = kxd * h_lo + cxd, qxb = kxd * h_hi + cxd;
     const double qya = kyd * h_lo + cyd, qyb = kyd * h_hi + cyd;
-    const double cz = (double)me[11] - (double)g.lower[2];
+    const double czd = (double)me[11] - (double)g.lower[2];
     const double dz = u32 * (S[2] + fabs((double)g.lower[2])) + 1e-30;
-    const double tz_a = kap[2] * h_lo + cz, tz_b = kap[2] * h_hi + cz;
+    const double tz_a = kap[2] * h_lo + czd, tz_b = kap[2] * h_hi + czd;
     const bool z_in = fmin(tz_a, tz_b) - dz > (double)g.zt_lo && fmax(tz_a, tz_b) + dz < (double)g.zt_hi;
     const bool z_out = fmax(tz_a, tz_b) + dz < (double)g.zt_lo || fmin(tz_a, tz_b) - dz > (double)g.zt_hi;
     const double big = fmax(fmax(fabs((double)pv0), fabs((double)pv1)), fabs((double)pv2)) * rho;
@@ -394,10 +402,103 @@ struct LinearWalk {
     const bool out = tame && (z_out || fmin(qxa, qxb) - ddx > (double)g.X || fmax(qxa, qxb) + ddx < -1.0 ||
                               fmin(qya, qyb) - ddy > (double)g.Y || fmax(qya, qyb) + ddy < -1.0);
     const double qmax = fmax(fmax(fabs(qxa), fabs(qxb)), fmax(fabs(qya), fabs(qyb)));
-    const bool lin = tame && z_in && ddx < 0.25 && ddy < 0.25 && qmax < 2.0e6;
-    mode = out ? 2 : (lin ? 1 : 0);
+    const bool lin = tame && ddx < 0.25 && ddy < 0.25 && qmax < 2.0e6;
+    // per-bin z test: one more rounding in fma(hgt, kz, cz) and in the thresholds themselves, covered by 2 dz
+    kz = (float)kap[2]; cz = (float)czd;
+    const double dz2 = 2.0 * dz + 1e-6 * dz;
+    z_in_lo = (float)((double)g.zt_lo + dz2); z_in_hi = (float)((double)g.zt_hi - dz2);
+    z_out_lo = (float)((double)g.zt_lo - dz2); z_out_hi = (float)((double)g.zt_hi + dz2);
+    const bool z_lin = dz2 < 0.25 * (double)g.size[2] && fabs(tz_a) < 1e30 && fabs(tz_b) < 1e30;
+    mode = out ? 2 : (lin && z_in ? 1 : (lin && z_lin ? 3 : 0));
   }
 };
+
+constexpr unsigned kWalkMagicBits = 0x4B400000u;  // 1.5 * 2^23
+
+// exact chain for one bin, kept out of line: it runs for ~0.5 % of the bins (guard band) and for the pixels the
+// linear form does not cover
+template <int ARITH>
+__device__ __noinline__ int fast_ray_voxel_noinline(const FastRay<ARITH> *ray, const float *a2, const float *me, float ref_h,
+                                                    int check_finite, const Grid *g, float z, int *bad) {
+  bool b = *bad != 0;
+  const int v = ray->voxel(a2, me, ref_h, check_finite != 0, *g, z, b);
+  *bad = b ? 1 : 0;
+  return v;
+}
+
+// Walk the D height bins of one pixel of a camera that qualifies for the fast path (camera_is_fast) and hand every
+// bin whose voxel differs from its predecessor's to `emit(d, voxel)` (consecutive equal voxels are reported once or
+// more often -- the caller's run builder compares again).  zs: bin values, hs: per-camera height table
+// hgt_d = RN(ref_h - p0z_d) valid iff h_uniform (row 2 of ida^-1 ignores u, v); both in shared memory.
+// Returns false when a point left the domain in which the shortcuts are proven exact (caller redoes the pixel's
+// block with the general chain).
+template <int ARITH, typename Emit>
+__device__ __forceinline__ bool walk_fast(const Camera &cam, const Grid &grid, const float *zs, const float *hs,
+                                          bool h_uniform, int D, float u, float v, float zmin, float zmax, Emit emit) {
+  FastRay<ARITH> ray;
+  int bad = ray.init(cam, u, v, zs[0]) ? 0 : 1;
+  float a2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a2[i] = cam.A[8 + i];
+  const float *mer = cam.Me;
+  const float rh = cam.ref_h;
+  const int check_finite = cam.has_bda;
+  LinearWalk lw;
+  {
+    const float pa = dot2_tail<ARITH>(ray.head2, a2, zmin, 1.0f);
+    const float pb = dot2_tail<ARITH>(ray.head2, a2, zmax, 1.0f);
+    lw.init(ray.pv0, ray.pv1, ray.pv2, mer, rh, fminf(pa, pb), fmaxf(pa, pb), grid);
+  }
+  const int mode = bad ? 0 : lw.mode;
+  if (mode == 1 || mode == 3) {
+    const float kx = lw.kx, cx = lw.cx, thx = lw.thx, ky = lw.ky, cy = lw.cy, thy = lw.thy;
+    const float magic = __uint_as_float(kWalkMagicBits);
+    const bool zchk = mode == 3;
+    const float kz = lw.kz, cz = lw.cz, zil = lw.z_in_lo, zih = lw.z_in_hi, zol = lw.z_out_lo, zoh = lw.z_out_hi;
+    float ptx = -1.0f, pty = -1.0f;   // t values are >= 2^22: -1 never matches
+    auto bin = [&](int d, float hgt) {
+      const float qx = __fmaf_rn(hgt, kx, cx), qy = __fmaf_rn(hgt, ky, cy);
+      const float tx = __fadd_rn(qx, magic), ty = __fadd_rn(qy, magic);
+      const float ex = __fsub_rn(qx, __fsub_rn(tx, magic)), ey = __fsub_rn(qy, __fsub_rn(ty, magic));
+      bool z_unsafe = false;
+      if (zchk) {
+        const float tz = __fmaf_rn(hgt, kz, cz);
+        const bool zin = tz > zil && tz < zih, zout = tz < zol || tz > zoh;
+        z_unsafe = !(zin || zout);
+        if (zout) {   // dropped for sure, whatever x / y say (an x / y guard-band hit cannot bring the point back)
+          emit(d, -1);
+          ptx = pty = -1.0f;
+          return;
+        }
+      }
+      if (fabsf(ex) > thx || fabsf(ey) > thy || z_unsafe) {
+        // within the guard band of a voxel boundary: the reference's own fp32 chain decides this bin
+        emit(d, fast_ray_voxel_noinline<ARITH>(&ray, a2, mer, rh, check_finite, &grid, zs[d], &bad));
+        ptx = pty = -1.0f;
+      } else if (tx != ptx || ty != pty) {
+        ptx = tx; pty = ty;
+        int ix = (int)(__float_as_uint(tx) - kWalkMagicBits), iy = (int)(__float_as_uint(ty) - kWalkMagicBits);
+        ix = ix == -1 ? 0 : ix;   // truncation toward zero: (-1, 0) belongs to index 0
+        iy = iy == -1 ? 0 : iy;
+        emit(d, ((unsigned)ix < (unsigned)grid.X && (unsigned)iy < (unsigned)grid.Y) ? iy * grid.X + ix : -1);
+      }
+    };
+    // the per-camera height table is this pixel's too iff its (u, v) part of row 2 is a zero
+    if (h_uniform && ray.head2 == 0.0f) {
+      for (int d = 0; d < D; ++d) bin(d, hs[d]);
+    } else {
+      const float head2 = ray.head2;
+      for (int d = 0; d < D; ++d) {
+        const float p0z = dot2_tail<ARITH>(head2, a2, zs[d], 1.0f);
+        bin(d, __fadd_rn(__fmul_rn(-1.0f, p0z), rh));
+      }
+    }
+  } else if (mode == 0) {
+    for (int d = 0; d < D; ++d)
+      emit(d, fast_ray_voxel_noinline<ARITH>(&ray, a2, mer, rh, check_finite, &grid, zs[d], &bad));
+  }
+  return bad == 0;
+}
 
 // :487-488  ((g - lower) / size).int() -- fp32 subtract, IEEE divide, cvt.rzi.s32.f32
 // (truncation toward zero, saturating, NaN -> 0: what `.int()` does on a CUDA tensor).

@@ -192,7 +192,8 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
   __shared__ geom::Camera cam;
   __shared__ int s_fast, s_zmin, s_zmax;  // z range of the bins as order-preserving ints
   extern __shared__ float z_s[];
-  int *s_hist = reinterpret_cast<int *>(z_s + m.D);
+  float *h_s = z_s + m.D;
+  int *s_hist = reinterpret_cast<int *>(z_s + 2 * m.D);
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int bn = b * m.Nc + n;
@@ -222,39 +223,23 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
     if (t == 0) chunk_done[frame_chunk] = 0;
     return;
   }
+  // per-camera table of the bins' heights above their planes (valid when row 2 of ida^-1 ignores u, v)
+  const bool h_uniform = cam.A[8] == 0.0f && cam.A[9] == 0.0f;
+  if (h_uniform) {
+    for (int d = t; d < m.D; d += kChunk) {
+      const float p0z = geom::dot2_tail<ARITH>(0.0f, cam.A + 8, z_s[d], 1.0f);
+      h_s[d] = __fadd_rn(__fmul_rn(-1.0f, p0z), cam.ref_h);
+    }
+  }
+  __syncthreads();
   const int p = ci * kChunk + t;
   int r = 0;
   bool bad = false;
   if (p < m.P) {
     const int h = p / m.fW, w = p - h * m.fW;
-    geom::FastRay<ARITH> ray;
-    bad = !ray.init(cam, u_tab[w], v_tab[h], z_s[0]);
-    float a2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a2[i] = cam.A[8 + i];
-    const float *mer = cam.Me;  // shared memory: only the (rare) exact chain reads it
-    const float rh = cam.ref_h;
-    const bool check_finite = cam.has_bda != 0;
-    // linear shortcut: p0z is monotone in z for every evaluation order, so its range over the bins is
-    // spanned by the two extreme bin values
-    geom::LinearGuard lg;
-    {
-      int za = s_zmin, zb = s_zmax;
-      za ^= (za >> 31) & 0x7fffffff;
-      zb ^= (zb >> 31) & 0x7fffffff;
-      const float pa = geom::dot2_tail<ARITH>(ray.head2, a2, __int_as_float(za), 1.0f);
-      const float pb = geom::dot2_tail<ARITH>(ray.head2, a2, __int_as_float(zb), 1.0f);
-      lg.init(ray.pv0, ray.pv1, ray.pv2, mer, rh, fminf(pa, pb), fmaxf(pa, pb), grid);
-      if (bad) lg.ok = false;
-    }
-    auto voxel_of_bin = [&](float z) -> int {
-      const float p0z = geom::dot2_tail<ARITH>(ray.head2, a2, z, 1.0f);
-      const float hgt = __fadd_rn(__fmul_rn(-1.0f, p0z), rh);
-      bool safe;
-      int v = lg.voxel(hgt, grid, safe);
-      if (!(lg.ok && safe)) v = ray.voxel(a2, mer, rh, check_finite, grid, z, bad);
-      return v;
-    };
+    int za = s_zmin, zb = s_zmax;
+    za ^= (za >> 31) & 0x7fffffff;
+    zb ^= (zb >> 31) & 0x7fffffff;
     int cur = -1, d0 = 0;
     // this chunk's block of the ELL table; run r of this pixel sits at element r * kChunk + t
     int *const rv = run_vox + ell_slot(frame_chunk, m.D, 0, 0);
@@ -273,19 +258,10 @@ ls_plan_runs_fast_kernel(Dims m, const float *__restrict__ u_tab, const float *_
         d0 = d;
       }
     };
-    int d = 0;
-    for (; d + 2 <= m.D; d += 2) {
-      const int v0 = voxel_of_bin(z_s[d]);
-      const int v1 = voxel_of_bin(z_s[d + 1]);
-      if (v0 != cur || v1 != cur) {  // one divergent region per pair of bins
-        step(d, v0);
-        step(d + 1, v1);
-      }
-    }
-    if (d < m.D) {
-      step(d, voxel_of_bin(z_s[d]));
-      ++d;
-    }
+    // guarded linear walk (geometry.cuh: walk_fast / LinearWalk): ~16 instructions per bin, the exact chain only inside
+    // the guard band of a voxel boundary
+    bad = !geom::walk_fast<ARITH>(cam, grid, z_s, h_s, h_uniform, m.D, u_tab[w], v_tab[h], __int_as_float(za),
+                                  __int_as_float(zb), step);
     step(m.D, -2);  // sentinel closes the last run
   }
   run_cnt[(size_t)frame_chunk * kChunk + t] = r;
@@ -1746,6 +1722,11 @@ geom::Grid make_grid(const Dims &m, const float *lower3, const float *size3) {
 
 using namespace sgv3d;
 
+extern "C" int sgv3d_lift_splat_uses_block_pipeline(const sgv3d_lift_splat_desc *desc) {
+  if (validate(desc, "lift_splat_uses_block_pipeline") != SGV3D_OK) return 0;
+  return use_block(desc, make_dims(desc)) ? 1 : 0;
+}
+
 extern "C" size_t sgv3d_lift_splat_workspace_bytes(const sgv3d_lift_splat_desc *desc) {
   if (validate(desc, "lift_splat_workspace_bytes") != SGV3D_OK || desc->B == 0) return 0;
   const Dims m = make_dims(desc);
@@ -1778,9 +1759,10 @@ extern "C" int sgv3d_lift_splat_plan(const sgv3d_lift_splat_desc *desc, const fl
   dim3 gc(m.nchunks, m.B);
   const int gen_grid = std::min(m.nchunks * m.B, 5 * kNumSMs);  // 5 CTAs of the general kernel fit on an SM
   const size_t zsm = sizeof(float) * m.D + sizeof(int) * m.ntiles;
+  const size_t zsm_fast = zsm + sizeof(float) * m.D;
 #define SGV3D_PLAN_RUNS(A)                                                                                  \
   do {                                                                                                      \
-    ls_plan_runs_fast_kernel<A><<<gc, kChunk, zsm, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego,   \
+    ls_plan_runs_fast_kernel<A><<<gc, kChunk, zsm_fast, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego,   \
                                                         bda, ref_heights, grid, w.run_cnt, w.run_vox,       \
                                                         w.run_d, w.hist, w.chunk_done);                     \
     SGV3D_CHECK_LAUNCH("ls_plan_runs_fast_kernel");                                                         \

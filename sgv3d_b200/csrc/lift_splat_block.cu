@@ -42,7 +42,6 @@ namespace {
 
 constexpr int kBP = 64;                 // pixels per block (8 x 8)
 constexpr int kFwdThreads = 8 * kBP;    // 8 lanes per pixel
-constexpr unsigned kMagicBits = 0x4B400000u;  // 1.5 * 2^23
 constexpr int kSlotShift = 18, kDMask = 511;  // run descriptor: d0 | d1 << 9 | slot << 18
 
 struct BDims {
@@ -218,51 +217,7 @@ bp_plan_kernel(BDims m, const float *__restrict__ u_tab, const float *__restrict
         ray.init(cam, u, v);
         for (int d = 0; d < m.D; ++d) step(d, ray.voxel(cam, grid, zs[d]));
       } else {
-        geom::FastRay<ARITH> ray;
-        bad = !ray.init(cam, u, v, zs[0]);
-        float a2[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a2[i] = cam.A[8 + i];
-        const float *mer = cam.Me;
-        const float rh = cam.ref_h;
-        const bool check_finite = cam.has_bda != 0;
-        geom::LinearWalk lw;
-        {
-          const float pa = geom::dot2_tail<ARITH>(ray.head2, a2, zmin, 1.0f);
-          const float pb = geom::dot2_tail<ARITH>(ray.head2, a2, zmax, 1.0f);
-          lw.init(ray.pv0, ray.pv1, ray.pv2, mer, rh, fminf(pa, pb), fmaxf(pa, pb), grid);
-          if (bad) lw.mode = 0;
-        }
-        // the per-camera height table is this pixel's too iff its (u, v) part of row 2 is a zero
-        const bool use_hs = h_uniform && ray.head2 == 0.0f;
-        auto hgt_of = [&](int d) -> float {
-          if (use_hs) return hs[d];
-          const float p0z = geom::dot2_tail<ARITH>(ray.head2, a2, zs[d], 1.0f);
-          return __fadd_rn(__fmul_rn(-1.0f, p0z), rh);
-        };
-        if (lw.mode == 1) {
-          const float magic = __uint_as_float(kMagicBits);
-          float ptx = -1.0f, pty = -1.0f;   // t values are >= 2^22: -1 never matches
-          for (int d = 0; d < m.D; ++d) {
-            const float hgt = hgt_of(d);
-            const float qx = __fmaf_rn(hgt, lw.kx, lw.cx), qy = __fmaf_rn(hgt, lw.ky, lw.cy);
-            const float tx = __fadd_rn(qx, magic), ty = __fadd_rn(qy, magic);
-            const float ex = __fsub_rn(qx, __fsub_rn(tx, magic)), ey = __fsub_rn(qy, __fsub_rn(ty, magic));
-            if (fabsf(ex) > lw.thx || fabsf(ey) > lw.thy) {
-              // within the guard band of a voxel boundary: the reference's own fp32 chain decides this bin
-              step(d, ray.voxel(a2, mer, rh, check_finite, grid, zs[d], bad));
-              ptx = pty = -1.0f;
-            } else if (tx != ptx || ty != pty) {
-              ptx = tx; pty = ty;
-              int ix = (int)(__float_as_uint(tx) - kMagicBits), iy = (int)(__float_as_uint(ty) - kMagicBits);
-              ix = ix == -1 ? 0 : ix;   // truncation toward zero: (-1, 0) belongs to index 0
-              iy = iy == -1 ? 0 : iy;
-              step(d, ((unsigned)ix < (unsigned)grid.X && (unsigned)iy < (unsigned)grid.Y) ? iy * grid.X + ix : -1);
-            }
-          }
-        } else if (lw.mode == 0) {
-          for (int d = 0; d < m.D; ++d) step(d, ray.voxel(a2, mer, rh, check_finite, grid, zs[d], bad));
-        }
+        bad = !geom::walk_fast<ARITH>(cam, grid, zs, hs, h_uniform, m.D, u, v, zmin, zmax, step);
       }
       step(m.D, -2);  // sentinel closes the last run
     }

@@ -21,7 +21,36 @@ __all__ = ["patch_view_transform", "unpatch_view_transform"]
 
 
 def _is_bsm(backbone) -> bool:
-    return type(backbone).__name__.upper().startswith("BSM")
+    """Structural test: LSSFPN owns an ``assist_layer`` conv (lss_fpn.py:301) and its ``height_net`` returns one
+    tensor; BSMLSSFPN has no ``assist_layer`` and its ``height_net`` is an ``MSCThead`` returning
+    (height, semantic1, context1, semantic0) (bsm_lss_fpn.py:214,362,376).  A class name containing "BSM" anywhere in
+    the MRO is the tie-breaker for modules that carry neither marker."""
+    if hasattr(backbone, "assist_layer"):
+        return False
+    if type(getattr(backbone, "height_net", None)).__name__ == "MSCThead":
+        return True
+    return any("BSM" in k.__name__.upper() for k in type(backbone).__mro__)
+
+
+def _base_voxel_net_hook(backbone) -> bool:
+    """True when ``_forward_voxel_net`` is the reference's identity hook (lss_fpn.py:403-404, bsm_lss_fpn.py:462-463): a
+    subclass that overrides it transforms the frustum tensor this path never materialises."""
+    fn = getattr(type(backbone), "_forward_voxel_net", None)
+    if fn is None:
+        return True
+    import ast
+    import inspect
+    import textwrap
+    try:
+        tree = ast.parse(textwrap.dedent(inspect.getsource(fn)))
+    except (OSError, TypeError, SyntaxError):
+        return False
+    f = tree.body[0]
+    if not isinstance(f, ast.FunctionDef) or len(f.args.args) != 2:
+        return False
+    stmts = [st for st in f.body if not (isinstance(st, ast.Expr) and isinstance(st.value, ast.Constant))]   # drop a docstring
+    return (len(stmts) == 1 and isinstance(stmts[0], ast.Return) and isinstance(stmts[0].value, ast.Name)
+            and stmts[0].value.id == f.args.args[1].arg)     # `return img_feat_with_height`
 
 
 def _lssfpn_single_sweep(self, sweep_index, sweep_imgs, mats_dict):
@@ -33,6 +62,7 @@ def _lssfpn_single_sweep(self, sweep_index, sweep_imgs, mats_dict):
                                               source_features.shape[3], source_features.shape[4])
     assist_features = self.assist_layer(source_features)
     height_feature = self._forward_height_net(source_features, mats_dict)
+    _sync_buffers(self)
     # lss_fpn.py:462-495, fused
     feature_map = self._sgv3d_lift_splat.forward_single_sweep(height_feature, mats_dict, sweep_index)
     if self.is_train_height:
@@ -44,6 +74,7 @@ def _bsm_single_sweep(self, sweep_index, sweep_imgs, mats_dict):
     # bsm_lss_fpn.py:510-522, unchanged behaviour
     img_feats = self.get_cam_feats(sweep_imgs)
     out = self._forward_height_net(img_feats, mats_dict)  # height, semantic1, context1, semantic0
+    _sync_buffers(self)
     # bsm_lss_fpn.py:523-559, fused
     feature_map = self._sgv3d_lift_splat.forward_single_sweep_bsm(out[0], out[1], out[2], mats_dict, sweep_index)
     if self.is_train_height:
@@ -51,9 +82,25 @@ def _bsm_single_sweep(self, sweep_index, sweep_imgs, mats_dict):
     return feature_map
 
 
-def patch_view_transform(backbone, arith=None, cache_plan: bool = False):
-    """Rebind ``backbone._forward_single_sweep`` to the fused path.  ``cache_plan=True`` re-uses the sorted
-    voxel-run index while the calibration tensors are unchanged (static roadside camera, inference)."""
+def _sync_buffers(backbone) -> None:
+    """Re-read the four registered buffers of the reference module (a ``load_state_dict`` after patching may have
+    replaced their values); cheap identity / version check per call, no device sync."""
+    ls = backbone._sgv3d_lift_splat
+    src = (backbone.frustum, backbone.voxel_coord, backbone.voxel_size, backbone.voxel_num)
+    sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in src)
+    if sig != backbone.__dict__.get("_sgv3d_buffer_sig"):
+        new = LiftSplat.from_buffers(*src, ls.output_channels, arith=ls.arith, cache_plan=ls.cache_plan)
+        object.__setattr__(backbone, "_sgv3d_lift_splat", new.to(backbone.frustum.device))
+        object.__setattr__(backbone, "_sgv3d_buffer_sig", sig)
+
+
+def patch_view_transform(backbone, arith=None, cache_plan: bool = False, is_bsm=None):
+    """Rebind ``backbone._forward_single_sweep`` to the fused path.  ``cache_plan=True`` re-uses the voxel-run plan
+    while the calibration tensors are unchanged (static roadside camera, inference).  ``is_bsm`` overrides the
+    structural LSSFPN / BSMLSSFPN detection."""
+    if not _base_voxel_net_hook(backbone):
+        raise RuntimeError(f"{type(backbone).__name__} overrides _forward_voxel_net: the fused path never builds the "
+                           "frustum tensor that hook transforms; refusing to patch")
     for name in ("frustum", "voxel_coord", "voxel_size", "voxel_num", "output_channels"):
         if not hasattr(backbone, name):
             raise RuntimeError(f"{type(backbone).__name__} has no attribute {name!r}: not an LSSFPN-like module")
@@ -64,7 +111,11 @@ def patch_view_transform(backbone, arith=None, cache_plan: bool = False):
     object.__setattr__(backbone, "_sgv3d_lift_splat", ls)
     if "_forward_single_sweep" not in backbone.__dict__:
         object.__setattr__(backbone, "_sgv3d_original_single_sweep", backbone._forward_single_sweep)
-    fn = _bsm_single_sweep if _is_bsm(backbone) else _lssfpn_single_sweep
+    object.__setattr__(backbone, "_sgv3d_buffer_sig",
+                       tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in
+                             (backbone.frustum, backbone.voxel_coord, backbone.voxel_size, backbone.voxel_num)))
+    bsm = _is_bsm(backbone) if is_bsm is None else bool(is_bsm)
+    fn = _bsm_single_sweep if bsm else _lssfpn_single_sweep
     object.__setattr__(backbone, "_forward_single_sweep", types.MethodType(fn, backbone))
     return backbone
 

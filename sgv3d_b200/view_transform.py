@@ -236,8 +236,10 @@ class _Geometry:
         self.D, self.fH, self.fW = gc.D, gc.fH, gc.fW
         ida_inv, m_virtual, m_ego = camera_matrices(sensor2ego, sensor2virtual, intrin, ida)
         self.ida_inv, self.m_virtual, self.m_ego = (_f32c(t, dev) for t in (ida_inv, m_virtual, m_ego))
-        self.ref_h = _f32c(reference_heights, dev).reshape(-1)
-        self.bda = _f32c(bda, dev)
+        # private copies: update_calibration() overwrites these in place and must never write through to the
+        # caller's reference_heights / bda_mat tensors
+        self.ref_h = _f32c(reference_heights, dev).reshape(-1).clone()
+        self.bda = _f32c(bda, dev).clone() if bda is not None else None
 
     def pointer_args(self):
         gc = self.gc
@@ -544,16 +546,26 @@ class LiftSplat(nn.Module):
                 m["reference_heights"][:, sweep_index, ...], m.get("bda_mat", None))
         c = channels or self.output_channels
         key = None
-        if self.cache_plan:
-            key = (c, ctx_dtype) + tuple(None if a is None else (a.data_ptr(), a._version, tuple(a.shape))
-                                         for a in args)
-            if key in self._plan_cache:
-                return self._plan_cache[key]
+        # The cache is keyed on the identity of the calibration tensors (storage address, version counter, shape) AND
+        # keeps those tensors alive next to the plan: while they live no other tensor can be allocated at their address,
+        # and an in-place update bumps the version, so an equal key implies equal values.  Never used during stream
+        # capture (a captured step must contain its own plan kernels).
+        capturing = args[0].is_cuda and torch.cuda.is_current_stream_capturing()
+        if self.cache_plan and not capturing:
+            key = (c, ctx_dtype, _DEFAULT_PIPELINE) + tuple(
+                None if a is None else (a.data_ptr(), a._version, tuple(a.shape), tuple(a.stride()), a.dtype) for a in args)
+            hit = self._plan_cache.get(key)
+            if hit is not None:
+                return hit[0]
         plan = LiftSplatPlan(self.frustum, *args, self.voxel_coord, self.voxel_size, self._grid, c, ctx_dtype,
                              self.arith, grid_const=self._const(args[0].device))
         if key is not None:
-            self._plan_cache = {key: plan}
+            self._plan_cache = {key: (plan, args)}
         return plan
+
+    def invalidate_plan_cache(self) -> None:
+        """Drop the cached plan (``cache_plan=True``), e.g. after re-calibrating a static camera out of band."""
+        self._plan_cache = {}
 
     # -- call sites ---------------------------------------------------------------------------------
     def forward_single_sweep(self, height_feature: torch.Tensor, mats_dict, sweep_index: int = 0) -> torch.Tensor:
@@ -595,7 +607,9 @@ class LiftSplatGraph:
     needs to run them.  Inference only (no autograd).  The captured graph reads the tensors handed to
     the constructor (``height_feature`` and every entry of ``mats_dict``); ``__call__`` optionally
     copies new values into them first, and returns the (B, C, Y, X) BEV map, which is overwritten by
-    the next call.  Geometry is recomputed on every replay, so the calibration may change per call.
+    the next call.  Geometry is recomputed on every replay, so the calibration may change per call (the plan
+    cache of ``LiftSplat(cache_plan=True)`` is bypassed during capture).  Which ``mats_dict`` entries exist
+    (``bda_mat`` present or ``None``), their shapes and dtypes are fixed at capture time; ``__call__`` raises on a mismatch.
     """
 
     def __init__(self, module: LiftSplat, height_feature: torch.Tensor, mats_dict, sweep_index: int = 0,
@@ -646,7 +660,16 @@ class LiftSplatGraph:
             if self.static_calibration:
                 raise RuntimeError("static_calibration graph: call refresh_calibration(mats_dict) to change the matrices")
             for k, v in mats_dict.items():
-                if v is not None and self.mats_dict.get(k) is not None:
-                    self.mats_dict[k].copy_(v, non_blocking=True)
+                have = self.mats_dict.get(k)
+                if v is None and have is None:
+                    continue
+                # whether an entry (e.g. bda_mat) is present is fixed at capture time: the graph has no buffer otherwise
+                if (v is None) != (have is None):
+                    raise RuntimeError(f"LiftSplatGraph: mats_dict[{k!r}] was {'absent' if have is None else 'present'} "
+                                       f"at capture and cannot be {'added' if have is None else 'removed'} on replay")
+                if tuple(v.shape) != tuple(have.shape) or v.dtype != have.dtype:
+                    raise RuntimeError(f"LiftSplatGraph: mats_dict[{k!r}] is {tuple(v.shape)} {v.dtype}, captured "
+                                       f"{tuple(have.shape)} {have.dtype}")
+                have.copy_(v, non_blocking=True)
         self.graph.replay()
         return self.bev

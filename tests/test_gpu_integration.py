@@ -134,3 +134,99 @@ def test_patched_bsm_module(grad):
 def test_patch_rejects_modules_that_are_not_lssfpn_like():
     with pytest.raises(RuntimeError, match="not an LSSFPN-like module"):
         patch_view_transform(nn.Linear(2, 2))
+
+
+def test_patch_refuses_an_overridden_voxel_net_hook_and_detects_bsm_structurally():
+    """a subclass overriding _forward_voxel_net (lss_fpn.py:419-420) would be silently ignored by the fused
+    path -> refuse; BSM is detected by structure (no assist_layer / MSCThead), not by the class name prefix."""
+    from sgv3d_b200.integration import _is_bsm
+    shape = get_shape("small")
+
+    class Hooked(LSSFPNStandIn):
+        def _forward_voxel_net(self, x):
+            return x * 2.0
+
+    with pytest.raises(RuntimeError, match="_forward_voxel_net"):
+        patch_view_transform(Hooked(shape).cuda())
+
+    class Identity(LSSFPNStandIn):
+        def _forward_voxel_net(self, img_feat_with_height):
+            return img_feat_with_height
+
+    patch_view_transform(Identity(shape).cuda())
+
+    class RenamedHead(BSMLSSFPNStandIn):     # a BSM subclass under another name, as the advisor describes
+        pass
+    RenamedHead.__name__ = "MyHead"
+    assert _is_bsm(RenamedHead(shape)) and not _is_bsm(LSSFPNStandIn(shape))
+    assert _is_bsm(LSSFPNStandIn(shape)) is False
+    m = patch_view_transform(LSSFPNStandIn(shape).cuda(), is_bsm=False)
+    assert m._forward_single_sweep.__func__.__name__ == "_lssfpn_single_sweep"
+
+
+def test_patched_module_follows_a_later_load_state_dict():
+    """buffers cloned at patch time must not go stale -- load_state_dict with another grid after patching."""
+    shape = get_shape("small")
+    torch.manual_seed(5)
+    mod = LSSFPNStandIn(shape).cuda()
+    patch_view_transform(mod)
+    md, imgs = _inputs(shape, 1)
+    a = mod._forward_single_sweep(0, imgs, md).detach().clone()
+    sd = {k: v.clone() for k, v in mod.state_dict().items()}
+    sd["voxel_coord"] = sd["voxel_coord"] + torch.tensor([0.8, 0.0, 0.0], device="cuda")   # grid shifted by half a voxel in x
+    mod.load_state_dict(sd)
+    b = mod._forward_single_sweep(0, imgs, md).detach()
+    assert not torch.equal(a, b)
+    d, c = mod.height_channels, mod.output_channels
+    want = _oracle_bev(mod, md, mod.captured[:, :d], mod.captured[:, d:d + c], shape.grid)
+    np.testing.assert_allclose(b.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_plan_cache_is_keyed_on_live_tensors_and_bypassed_under_capture():
+    """cache_plan must never return a plan built for other calibration values.  The cache keeps
+    the keyed tensors alive (so a new tensor cannot reuse their address), sees in-place updates through the version
+    counter, and is not consulted while a CUDA graph is being captured."""
+    from sgv3d_b200 import LiftSplat, LiftSplatGraph
+    from sgv3d_b200.synthetic import make_activations
+    shape = get_shape("small")
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim, shape.downsample,
+                    shape.channels, cache_plan=True).cuda()
+    ref = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim, shape.downsample,
+                    shape.channels).cuda()
+    logits, ctx = make_activations(shape, 2, 1, seed=3)
+    hf = torch.cat((logits, ctx), 1).cuda()
+
+    def md_of(seed):
+        mats = make_mats(shape, 2, 1, seed=seed, bda="identity")
+        return {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).cuda(), "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).cuda(),
+                "intrin_mats": mats["intrin"].unsqueeze(1).cuda(), "ida_mats": mats["ida"].unsqueeze(1).cuda(),
+                "reference_heights": mats["reference_heights"].unsqueeze(1).cuda(), "bda_mat": mats["bda"].cuda()}
+
+    with torch.no_grad():
+        for seed in range(90, 96):          # a fresh mats_dict per step: freed tensors may be re-allocated at the same address
+            md = md_of(seed)
+            assert torch.equal(mod.forward_single_sweep(hf, md), ref.forward_single_sweep(hf, md)), seed
+            del md
+        md = md_of(97)
+        a = mod.forward_single_sweep(hf, md)
+        p1 = mod.make_plan(md)
+        assert mod.make_plan(md) is p1                              # unchanged tensors: cache hit
+        md["reference_heights"].add_(0.25)                          # in-place update: version bump -> new plan
+        assert mod.make_plan(md) is not p1
+        assert torch.equal(mod.forward_single_sweep(hf, md), ref.forward_single_sweep(hf, md))
+        assert not torch.equal(mod.forward_single_sweep(hf, md), a)
+    # graph capture with cache_plan=True on the module: the plan kernels must be part of the graph
+    g = LiftSplatGraph(mod, hf.clone(), md_of(98))
+    md_b = md_of(99)
+    with torch.no_grad():
+        want_b = ref.forward_single_sweep(hf, md_b)
+    assert torch.equal(g(hf, md_b), want_b)                         # new calibration on replay is honoured
+    with pytest.raises(RuntimeError, match="bda_mat"):
+        g(hf, {**md_b, "bda_mat": None})
+    # refresh_calibration must not write through to the caller's tensors (ADVICE r1, low)
+    md_c, md_d = md_of(100), md_of(101)
+    keep = {k: v.clone() for k, v in md_c.items()}
+    gs = LiftSplatGraph(ref, hf.clone(), md_c, static_calibration=True)
+    gs.refresh_calibration(md_d)
+    for k in keep:
+        assert torch.equal(md_c[k], keep[k]), k

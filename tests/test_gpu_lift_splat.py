@@ -463,13 +463,12 @@ def test_fused_path_nan_and_inf_rays():
 
 
 def test_fused_path_frame_with_every_point_dropped_and_empty_batch():
-    """Frame 1 looks away from the grid (camera yawed by 180 degrees): no point is kept, its BEV map must be all
-    zeros and its gradients zero; frame 0 is a normal frame.  Then B = 0: empty outputs, no launch failure."""
+    """Frame 1 stands 1 km beyond the grid: no point is kept, its BEV map must be all zeros and its gradients zero;
+    frame 0 is a normal frame.  Then B = 0: empty outputs, no launch failure."""
     shape = get_shape("small")
     B = 2
     mats = make_mats(shape, B, 1, seed=52, bda="identity")
-    flip = torch.diag(torch.tensor([-1.0, -1.0, 1.0, 1.0]))
-    mats["sensor2ego"][1, 0] = flip @ mats["sensor2ego"][1, 0]
+    mats["sensor2ego"][1, 0, 0, 3] += 1000.0
     plan, fr, vs, vc, dev = _plan_from(shape, mats)
     idx = _indices_like_the_gpu(shape, fr, vs, vc, dev)
     X, Y, Z = shape.grid
