@@ -33,6 +33,8 @@
 // No floating-point atomics anywhere; every sum has a fixed order => bitwise reproducible.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "geometry.cuh"
@@ -1324,8 +1326,8 @@ ls_grad_rows_kernel(Dims m, const float *__restrict__ grad_bev, const int *__res
 constexpr int kBwdPix = 64;    // pixels per CTA (half a plan chunk)
 constexpr int kBwdLd = kBwdPix + 1;
 
-template <typename CT, int NV>
-__global__ void __launch_bounds__(kBwdPix * 4, 2)
+template <typename CT, int NV, int OCC>
+__global__ void __launch_bounds__(kBwdPix * 4, OCC)
 ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__restrict__ context,
                          const float *__restrict__ gT, const int *__restrict__ run_cnt,
                          const int *__restrict__ run_vox, const int *__restrict__ run_d,
@@ -1621,10 +1623,22 @@ template <typename CT, int NV>
 int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *height, const void *context,
                               float *grad_height, float *grad_context, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)m.D * kBwdPix + (size_t)m.Cpad * kBwdLd);
-  if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV>, smem)) return rc;
-  ls_backward_chunk_kernel<CT, NV><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(
-      m, height, static_cast<const CT *>(context), w.gT, w.run_cnt, w.run_vox, w.run_d, w.w_pm, w.gw_pm,
-      grad_height, grad_context);
+  // CTAs per SM: the kernel is latency bound (dependent gather -> FMA -> shuffle chains), so a third resident CTA pays
+  // for the ~14 words of spill it costs at <= 80 channels (DAIR-R50: 440 -> 385 us at 64 frames); with 96-float rows
+  // the spills dominate (SGV3D-BSM-R50: 737 -> 1117 us), so those keep two.  SGV3D_BWD_OCC overrides (experiments).
+  static const int occ_env = getenv("SGV3D_BWD_OCC") ? atoi(getenv("SGV3D_BWD_OCC")) : 0;
+  const int occ = occ_env ? occ_env : (NV <= 3 ? 4 : (NV <= 5 ? 3 : 2));
+#define SGV3D_BWD_CHUNK(OCC)                                                                                   \
+  do {                                                                                                         \
+    if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC>, smem)) return rc;                             \
+    ls_backward_chunk_kernel<CT, NV, OCC><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(                 \
+        m, height, static_cast<const CT *>(context), w.gT, w.run_cnt, w.run_vox, w.run_d, w.w_pm, w.gw_pm,     \
+        grad_height, grad_context);                                                                            \
+  } while (0)
+  if (occ >= 4) SGV3D_BWD_CHUNK(4);
+  else if (occ == 3) SGV3D_BWD_CHUNK(3);
+  else SGV3D_BWD_CHUNK(2);
+#undef SGV3D_BWD_CHUNK
   SGV3D_CHECK_LAUNCH("ls_backward_chunk_kernel");
   return SGV3D_OK;
 }
@@ -1692,11 +1706,13 @@ int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, cons
              : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s);
 }
 
-// Which pipeline serves this descriptor: desc->reserved[0] = 0 (auto: the pixel-block pipeline of
-// lift_splat_block.cu when it supports the shape), 1 (voxel-tile pipeline of this file), 2 (pixel-block, required).
+// Which pipeline serves this descriptor: desc->reserved[0] = 0 (auto), 1 (voxel-tile pipeline of this file),
+// 2 (pixel-block pipeline of lift_splat_block.cu, required).  Auto = voxel-tile: measured on B200 (profiles/README.md,
+// round 2) it is the faster one for every reference shape -- DAIR-R50, 64 frames: plan + forward 452 vs 560 us,
+// backward 470 vs 790 us -- although the pixel-block pipeline plans in one kernel (125 vs 194 us) and moves
+// close to the algorithmic bytes; it stays selectable (tests run both) until its block kernels catch up.
 bool use_block(const sgv3d_lift_splat_desc *desc, const Dims &m) {
-  if (desc->reserved[0] == 1) return false;
-  return block::supported(m);
+  return desc->reserved[0] == 2 && block::supported(m);
 }
 // the pixel-block pipeline's workspace follows the voxel-tile pipeline's
 void *block_ws(void *workspace, const Dims &m, int ctx_dtype) {

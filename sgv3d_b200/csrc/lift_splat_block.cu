@@ -87,8 +87,7 @@ struct BWorkspace {
   int *vox;            // [B*NB][D][64]   voxel id of run r of pixel t
   int *rd;             // [B*NB][D][64]   d0 | d1 << 9 | slot << 18
   BlockInfo *info;     // [B*NB]
-  unsigned *fmask;     // [B*NB][nstrips] footprint bitmap
-  unsigned *fbase;     // [B*NB][nstrips] slot of the strip's first touched voxel
+  uint2 *ftab;         // [B*NB][nstrips] footprint: {bitmap of the strip, slot of its first touched voxel}
   int *alloc;          // [B] rows handed out per frame, then [B] overflow flags
   float *prow;         // [B][rows_cap][Cpad] partial sums
   float *gw;           // [B*NB][D][64] backward scratch: d BEV . ctx per run
@@ -103,8 +102,7 @@ BWorkspace carve(void *ws, const BDims &m) {
   w.vox = c.take<int>(nb * m.D * kBP);
   w.rd = c.take<int>(nb * m.D * kBP);
   w.info = reinterpret_cast<BlockInfo *>(c.take<int4>(nb));
-  w.fmask = c.take<unsigned>(nb * m.nstrips);
-  w.fbase = c.take<unsigned>(nb * m.nstrips);
+  w.ftab = c.take<uint2>(nb * m.nstrips);
   w.alloc = c.take<int>(2 * (size_t)m.B);
   w.prow = c.take<float>((size_t)m.B * m.rows_cap * m.Cpad);
   w.gw = c.take<float>(nb * m.D * kBP);
@@ -136,8 +134,7 @@ bp_plan_kernel(BDims m, const float *__restrict__ u_tab, const float *__restrict
                const float *__restrict__ z_tab, const float *__restrict__ ida_inv, const float *__restrict__ mv,
                const float *__restrict__ me, const float *__restrict__ bda, const float *__restrict__ ref_h,
                geom::Grid grid, int *__restrict__ cnt_out, int *__restrict__ vox_out, int *__restrict__ rd_out,
-               BlockInfo *__restrict__ info, unsigned *__restrict__ fmask, unsigned *__restrict__ fbase,
-               int *__restrict__ alloc) {
+               BlockInfo *__restrict__ info, uint2 *__restrict__ ftab, int *__restrict__ alloc) {
   __shared__ geom::Camera cam;
   __shared__ int s_flags[4];   // 0: camera qualifies for the fast path, 1: z table finite, 2: hgt table valid
   __shared__ int s_red[2][2];
@@ -269,11 +266,8 @@ bp_plan_kernel(BDims m, const float *__restrict__ u_tab, const float *__restrict
     info[fbk] = bi;
   }
   __syncthreads();
-  unsigned *gm = fmask + fbk * m.nstrips, *gbs = fbase + fbk * m.nstrips;
-  for (int i = t; i < m.nstrips; i += kBP) {
-    gm[i] = fm[i];
-    gbs[i] = fb[i];
-  }
+  uint2 *gt = ftab + fbk * m.nstrips;
+  for (int i = t; i < m.nstrips; i += kBP) gt[i] = make_uint2(fm[i], fb[i]);
   // slot of every run (each thread re-reads what it wrote itself)
   for (int r0 = 0; r0 < r; r0 += 4) {
     int vv[4], dd[4];
@@ -294,45 +288,61 @@ bp_plan_kernel(BDims m, const float *__restrict__ u_tab, const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// shared staging helpers of the forward / backward block kernels (512 threads: pixel t = tid >> 3, lane l = tid & 7)
+// shared helpers of the forward / backward block kernels (512 threads: pixel t = tid >> 3, lane l = tid & 7)
 // ---------------------------------------------------------------------------------------------
-// height bins (or logits) of the block: col[d * 64 + t]; pixels outside the image read as 0
-__device__ __forceinline__ void stage_block_columns(float *col, const float *__restrict__ src /*camera base*/,
-                                                    const BDims &m, int blk, bool vec16) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+__device__ __forceinline__ void cp_async_4_zfill(float *smem_dst, const float *gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;   // src-size 0: four zero bytes are written, the source is not read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct Org {   // image position of a pixel block
+  int h0, w0;
+  bool full;   // all 64 pixels inside the image
+};
+__device__ __forceinline__ Org block_origin(const BDims &m, int blk) {
   const int bi = blk / m.nbw, bj = blk - bi * m.nbw;
-  const int h0 = bi * 8, w0 = bj * 8;
-  const bool full = h0 + 8 <= m.fH && w0 + 8 <= m.fW;
-  if (vec16 && full) {
+  Org o;
+  o.h0 = bi * 8; o.w0 = bj * 8;
+  o.full = o.h0 + 8 <= m.fH && o.w0 + 8 <= m.fW;
+  return o;
+}
+
+// height bins (or logits) of the block: col[d * 64 + t]; pixels outside the image read as 0.  cp.async, not waited for.
+__device__ __forceinline__ void stage_block_columns(float *col, const float *__restrict__ src /*camera base*/,
+                                                    const BDims &m, const Org &o, bool vec16) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const float *base = src + o.h0 * m.fW + o.w0;
+  if (vec16 && o.full) {
     // item = (d, row, half): one 16-byte piece
-    const int items = m.D * 16;
-    for (int i = tid; i < items; i += nthr) {
-      const int d = i >> 4, row = (i >> 1) & 7, half = i & 1;
-      cp_async_16(col + d * kBP + row * 8 + half * 4, src + (size_t)d * m.P + (size_t)(h0 + row) * m.fW + w0 + half * 4);
-    }
+    const int row = (tid >> 1) & 7, half = tid & 1;
+    const int off = row * m.fW + half * 4, soff = row * 8 + half * 4;
+    for (int d = tid >> 4; d < m.D; d += nthr >> 4) cp_async_16(col + d * kBP + soff, base + (size_t)d * m.P + off);
   } else {
-    const int items = m.D * kBP;
-    for (int i = tid; i < items; i += nthr) {
-      const int d = i >> 6, t = i & 63;
-      const int h = h0 + (t >> 3), w = w0 + (t & 7);
-      if (h < m.fH && w < m.fW) cp_async_4(col + i, src + (size_t)d * m.P + (size_t)h * m.fW + w);
-      else col[i] = 0.0f;
-    }
+    const int t = tid & 63;
+    const int r = t >> 3, c = t & 7;
+    const bool ok = o.h0 + r < m.fH && o.w0 + c < m.fW;
+    const int off = r * m.fW + c;
+    for (int d = tid >> 6; d < m.D; d += nthr >> 6) cp_async_4_zfill(col + d * kBP + t, ok ? base + (size_t)d * m.P + off : src, ok);
   }
 }
 
 // softmax over D of pixel t's column by its 8 lanes (lane l takes d = l mod 8): leaves exp(x - max) in col and
 // returns 1 / sum.  Fixed butterfly order => deterministic, identical in forward and backward.
 __device__ __forceinline__ float softmax_block_column(float *col, int D, int t, int l, unsigned gmask) {
+  float *c0 = col + l * kBP + t;
   float mx = -INFINITY;
-  for (int d = l; d < D; d += 8) mx = fmaxf(mx, col[d * kBP + t]);
+  for (int d = l; d < D; d += 8) mx = fmaxf(mx, c0[(d - l) * kBP]);
   mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 1));
   mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 2));
   mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 4));
   float sm = 0.0f;
   for (int d = l; d < D; d += 8) {
-    const float e = exp_ex2(__fsub_rn(col[d * kBP + t], mx));
-    col[d * kBP + t] = e;
+    const float e = exp_ex2(__fsub_rn(c0[(d - l) * kBP], mx));
+    c0[(d - l) * kBP] = e;
     sm = __fadd_rn(sm, e);
   }
   sm = __fadd_rn(sm, __shfl_xor_sync(gmask, sm, 1));
@@ -341,15 +351,11 @@ __device__ __forceinline__ float softmax_block_column(float *col, int D, int t, 
   return __fdiv_rn(1.0f, sm);
 }
 
-// Row layout (shared memory and partial rows): element 4 * (k * 8 + l) + e of a row holds channel l + 8 * (4k + e)
-// (lane l of an 8-lane group owns NV float4: one 128-byte line per k and group).  In shared memory the 16-byte chunk
-// j = k * 8 + l of row i is stored at chunk (k * 8) + ((l ^ i) & 7): rows are 32 * NV words apart, i.e. all rows
-// start in bank 0, and the XOR spreads the same chunk of 8 consecutive rows over the 8 bank groups.
-__device__ __forceinline__ int row_chunk(int i, int k, int l) { return k * 8 + ((l ^ i) & 7); }
-__host__ __device__ __forceinline__ int chan_of(int k, int l, int e) { return l + 8 * (4 * k + e); }
-
-template <typename CT>
-__device__ __forceinline__ float ld_ctx(const CT *p) { return to_f32<CT>(*p); }
+// Rows (context rows, gradient rows, partial sums) hold the channels in natural order, 32 * NV floats per row; lane l
+// of an 8-lane group owns the 16-byte chunks l, 8 + l, 16 + l (channels 32k + 4l .. + 3).  In SHARED memory the chunk j
+// of row i sits at chunk position (j & ~7) | ((j ^ i) & 7): rows are a multiple of 32 words apart, so without the XOR
+// the same chunk of different rows would share its banks.
+__device__ __forceinline__ int swz(int j, int i) { return (j & ~7) | ((j ^ i) & 7); }
 
 struct BsmArgs {
   const float *sem;      // [B*Nc, Cs, fH, fW] semantic logits, or nullptr
@@ -358,28 +364,30 @@ struct BsmArgs {
   float thr;
 };
 
+// run weight: sum of the (exponentiated) bins d0 .. d1 - 1 of pixel t, ascending
+__device__ __forceinline__ float run_weight(const float *col, int t, int rdv) {
+  const int d0 = rdv & kDMask, d1 = (rdv >> 9) & kDMask;
+  const float *c = col + d0 * kBP + t;
+  float w = 0.0f;
+  for (int d = d0; d < d1; ++d, c += kBP) w = __fadd_rn(w, *c);
+  return w;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FORWARD.  grid (NB, B), 512 threads, dynamic smem: col [D][64] | rows [64][Cpad] | W [cap][64] | pm [cap][2] | sem
-// FIXUP: blocks whose partial rows did not fit the pool add their sums to the BEV map with atomics instead
-// (launched after the combine kernel; every other block exits at once).
 // ---------------------------------------------------------------------------------------------
-template <typename CT, int NV, bool FIXUP>
+template <typename CT, int NV>
 __global__ void __launch_bounds__(kFwdThreads, 2)
 bp_forward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16, const CT *__restrict__ context,
                   BsmArgs bsm, const int *__restrict__ cnt_in, const int *__restrict__ rd_in,
-                  const int *__restrict__ vox_in, const BlockInfo *__restrict__ info, const int *__restrict__ alloc,
-                  float *__restrict__ prow, float *__restrict__ bev) {
+                  const BlockInfo *__restrict__ info, float *__restrict__ prow) {
   constexpr int kCpad = 32 * NV;
   extern __shared__ __align__(16) float fsm[];
   __shared__ float s_keep[kBP];
   const int b = blockIdx.y, kb = blockIdx.x;
   const size_t fbk = (size_t)b * m.NB + kb;
   const BlockInfo bi = info[fbk];
-  if (FIXUP) {
-    if (bi.row_base >= 0) return;
-  } else {
-    if (bi.nslots == 0 || bi.row_base < 0) return;
-  }
+  if (bi.nslots == 0 || bi.row_base < 0) return;
   float *col = fsm;
   float *rows = col + m.D * kBP;
   float *Wm = rows + kBP * kCpad;
@@ -387,20 +395,22 @@ bp_forward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16,
   float *sem_s = reinterpret_cast<float *>(pm + 2 * cap);   // [Cs][64] (BSM only)
   const int n = kb / m.nblk, blk = kb - n * m.nblk;
   const int bn = b * m.Nc + n;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t = tid >> 3, l = tid & 7;
-  const unsigned gmask = 0xffu << ((tid & 31) & 24);
+  const unsigned gmask = 0xffu << (lane & 24);
+  const Org o = block_origin(m, blk);
 
-  stage_block_columns(col, height + (size_t)bn * m.hs, m, blk, vec16 != 0);
+  stage_block_columns(col, height + (size_t)bn * m.hs, m, o, vec16 != 0);
+  cp_async_commit();
   // BSM context assembly (bsm_lss_fpn.py:524-529): per-pixel softmax over the Cs semantic channels in torch's
   // order (max, sum of exp(x - max) in channel order, exp / sum), background mask
   const int Cc = m.C - (bsm.sem ? bsm.Cs : 0);
   if (bsm.sem) {
     if (tid < kBP) {
-      const Pix q = pixel_of(m, blk, tid);
+      const int h = o.h0 + (tid >> 3), w = o.w0 + (tid & 7);
       float keep = 1.0f;
-      if (q.valid) {
-        const float *ss = bsm.sem + (size_t)bn * bsm.sem_stride + q.p;
+      if (h < m.fH && w < m.fW) {
+        const float *ss = bsm.sem + (size_t)bn * bsm.sem_stride + h * m.fW + w;
         float mx = ss[0];
         for (int k = 1; k < bsm.Cs; ++k) mx = fmaxf(mx, ss[(size_t)k * m.P]);
         float sum = 0.0f;
@@ -415,81 +425,62 @@ bp_forward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16,
     }
     __syncthreads();
   }
-  // context rows: item = (pixel, 16-byte chunk j = k * 8 + l'): four channels l' + 8 (4k + e) of one pixel
+  // context rows: warp item = (image row r of the block, chunk j); lane = (pixel of the row, channel of the chunk):
+  // one request reads 4 channel planes x 32 bytes and writes one chunk of 8 rows (8 different bank groups)
   {
     const CT *cb = context + (size_t)bn * m.cs;
-    for (int i = tid; i < kBP * 8 * NV; i += kFwdThreads) {
-      const int tp = i & 63, j = i >> 6;
-      const int k = j >> 3, lp = j & 7;
-      const Pix q = pixel_of(m, blk, tp);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q.valid) {
-        float e[4];
-#pragma unroll
-        for (int ee = 0; ee < 4; ++ee) {
-          const int c = chan_of(k, lp, ee);
-          float x = 0.0f;
-          if (c < Cc) x = ld_ctx<CT>(cb + (size_t)c * m.P + q.p);
+    const int e = lane & 3, tpl = lane >> 2;
+    const bool wok = o.w0 + tpl < m.fW;
+    for (int it = wid; it < 8 * 8 * NV; it += kFwdThreads / 32) {
+      const int r = it & 7, j = it >> 3;
+      const int c = 4 * j + e, tp = r * 8 + tpl;
+      const bool ok = wok && o.h0 + r < m.fH;
+      float *dst = rows + tp * kCpad + 4 * swz(j, tp) + e;
+      const int off = c * m.P + (o.h0 + r) * m.fW + o.w0 + tpl;
+      if (sizeof(CT) == 4 && !bsm.sem) {
+        cp_async_4_zfill(dst, reinterpret_cast<const float *>(cb) + (ok && c < m.C ? off : 0), ok && c < m.C);
+      } else {
+        float x = 0.0f;
+        if (ok) {
+          if (c < Cc) x = to_f32<CT>(cb[off]);
           else if (c < m.C) x = sem_s[(c - Cc) * kBP + tp];
           if (bsm.sem) x = __fmul_rn(x, s_keep[tp]);
-          e[ee] = x;
         }
-        v = make_float4(e[0], e[1], e[2], e[3]);
+        *dst = x;
       }
-      *reinterpret_cast<float4 *>(rows + tp * kCpad + 4 * row_chunk(tp, k, lp)) = v;
     }
   }
-  cp_async_wait_all();
-  __syncthreads();
-
+  cp_async_commit();
   const int cnt = cnt_in[fbk * kBP + t];
+  const int *rdp = rd_in + fbk * m.D * kBP + t;
+  // this lane's first run descriptors travel while the columns land
+  int rd0 = 0, rd1 = 0;
+  if (l < cnt) rd0 = rdp[l * kBP];
+  if (l + 8 < cnt) rd1 = rdp[(l + 8) * kBP];
+  cp_async_wait_group<1>();   // columns
+  __syncthreads();
   float scale = 1.0f;
   if (m.logits) scale = softmax_block_column(col, m.D, t, l, gmask);
   const bool keep_px = !bsm.sem || s_keep[t] != 0.0f;   // masked pixels contribute exact zeros: skipped entirely
-  const int *rdp = rd_in + fbk * m.D * kBP;
-  const int *rvp = vox_in + fbk * m.D * kBP;
-  float *pr = FIXUP ? nullptr : prow + ((size_t)b * m.rows_cap + bi.row_base) * kCpad;
-  float *bevb = bev + (size_t)b * m.C * m.V;
+  float *pr = prow + ((size_t)b * m.rows_cap + bi.row_base) * kCpad;
+  cp_async_wait_group<0>();   // context rows
 
-  if constexpr (FIXUP) {
-    // degenerate path (partial-row pool exhausted): w * ctx_row of every run goes to the BEV map with global
-    // atomics, after the combine kernel has written it
-    if (keep_px) {
-      for (int r = l; r < cnt; r += 8) {
-        const int rdv = rdp[r * kBP + t];
-        const int vox = rvp[r * kBP + t];
-        const int d0 = rdv & kDMask, d1 = (rdv >> 9) & kDMask;
-        float w = 0.0f;
-        for (int d = d0; d < d1; ++d) w = __fadd_rn(w, col[d * kBP + t]);
-        if (m.logits) w = __fmul_rn(w, scale);
-        for (int j = 0; j < 8 * NV; ++j) {
-          const int k = j >> 3, lp = j & 7;
-          const float4 x = *reinterpret_cast<const float4 *>(rows + t * kCpad + 4 * row_chunk(t, k, lp));
-          const float xe[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = chan_of(k, lp, e);
-            if (c < m.C) atomicAdd(bevb + (size_t)c * m.V + vox, __fmul_rn(w, xe[e]));
-          }
-        }
-      }
-    }
-  } else {
   for (int lo = 0; lo < bi.nslots; lo += cap) {
     const int nr = min(cap, bi.nslots - lo);
-    for (int i = tid; i < nr * kBP; i += kFwdThreads) Wm[i] = 0.0f;
-    for (int i = tid; i < 2 * nr; i += kFwdThreads) pm[i] = 0u;
+    {
+      float4 *w4 = reinterpret_cast<float4 *>(Wm);
+      for (int i = tid; i < nr * (kBP / 4); i += kFwdThreads) w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < 2 * nr; i += kFwdThreads) pm[i] = 0u;
+    }
     __syncthreads();
     // run weights: lane l takes the runs r = l mod 8 of pixel t.  W[s][t] += w: a pixel meets a voxel once along its
     // ray, so this is a plain store in all but degenerate geometries (then two addends, which commute)
     if (keep_px) {
       for (int r = l; r < cnt; r += 8) {
-        const int rdv = rdp[r * kBP + t];
+        const int rdv = r == l ? rd0 : (r == l + 8 ? rd1 : rdp[r * kBP]);
         const int s = (int)((unsigned)rdv >> kSlotShift) - lo;
         if ((unsigned)s < (unsigned)nr) {
-          const int d0 = rdv & kDMask, d1 = (rdv >> 9) & kDMask;
-          float w = 0.0f;
-          for (int d = d0; d < d1; ++d) w = __fadd_rn(w, col[d * kBP + t]);
+          float w = run_weight(col, t, rdv);
           if (m.logits) w = __fmul_rn(w, scale);
           atomicAdd(&Wm[s * kBP + t], w);
           atomicOr(&pm[2 * s + (t >> 5)], 1u << (t & 31));
@@ -504,17 +495,18 @@ bp_forward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16,
       for (int k = 0; k < NV; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
+      const float *wrow = Wm + s * kBP;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         unsigned bits = pm[2 * s + half];
         while (bits) {
           const int tp = half * 32 + __ffs(bits) - 1;
           bits &= bits - 1;
-          const float w = Wm[s * kBP + tp];
-          const float *row = rows + tp * kCpad;
+          const float w = wrow[tp];
+          const float *row = rows + tp * kCpad + 4 * ((l ^ tp) & 7);
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
-            const float4 x = *reinterpret_cast<const float4 *>(row + 4 * row_chunk(tp, k, l));
+            const float4 x = *reinterpret_cast<const float4 *>(row + 32 * k);
             fma2(acc[k][0], acc[k][1], w, x.x, x.y);
             fma2(acc[k][2], acc[k][3], w, x.z, x.w);
           }
@@ -527,6 +519,72 @@ bp_forward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16,
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FIX-UP (degenerate path): blocks whose partial rows did not fit the frame's row pool add w * ctx of every run to the
+// BEV map with global atomics, after the combine kernel has written it.  A small persistent grid: it first looks at
+// the frames' overflow flags and normally exits at once.
+// ---------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(256)
+bp_fixup_kernel(BDims m, const float *__restrict__ height, const CT *__restrict__ context, BsmArgs bsm,
+                const int *__restrict__ cnt_in, const int *__restrict__ rd_in, const int *__restrict__ vox_in,
+                const BlockInfo *__restrict__ info, const int *__restrict__ alloc, float *__restrict__ bev) {
+  int any = 0;
+  for (int i = threadIdx.x; i < m.B; i += blockDim.x) any |= alloc[m.B + i];
+  if (!__syncthreads_or(any)) return;
+  const int Cc = m.C - (bsm.sem ? bsm.Cs : 0);
+  const int total = m.B * m.NB;
+  // warp per pixel-block pixel: plain, slow, correct
+  for (int fb = blockIdx.x; fb < total; fb += gridDim.x) {
+    if (info[fb].row_base >= 0) continue;
+    const int b = fb / m.NB, kb = fb - b * m.NB;
+    const int n = kb / m.nblk, blk = kb - n * m.nblk;
+    const int bn = b * m.Nc + n;
+    const Org o = block_origin(m, blk);
+    const float *hb = height + (size_t)bn * m.hs;
+    const CT *cb = context + (size_t)bn * m.cs;
+    float *bevb = bev + (size_t)b * m.C * m.V;
+    for (int t = threadIdx.x >> 5; t < kBP; t += blockDim.x >> 5) {
+      const int lane = threadIdx.x & 31;
+      const int h = o.h0 + (t >> 3), w = o.w0 + (t & 7);
+      if (h >= m.fH || w >= m.fW) continue;
+      const int p = h * m.fW + w;
+      const int cnt = cnt_in[(size_t)fb * kBP + t];
+      float keep = 1.0f, semp[16];
+      if (bsm.sem) {
+        const float *ss = bsm.sem + (size_t)bn * bsm.sem_stride + p;
+        float mx = ss[0];
+        for (int k = 1; k < bsm.Cs; ++k) mx = fmaxf(mx, ss[(size_t)k * m.P]);
+        float sum = 0.0f;
+        for (int k = 0; k < bsm.Cs; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(ss[(size_t)k * m.P], mx)));
+        for (int k = 0; k < bsm.Cs && k < 16; ++k) semp[k] = __fdiv_rn(expf(__fsub_rn(ss[(size_t)k * m.P], mx)), sum);
+        keep = semp[0] > bsm.thr ? 0.0f : 1.0f;
+      }
+      if (keep == 0.0f) continue;
+      float mx = -INFINITY, sm = 1.0f;
+      if (m.logits) {
+        for (int d = 0; d < m.D; ++d) mx = fmaxf(mx, hb[(size_t)d * m.P + p]);
+        sm = 0.0f;
+        for (int d = 0; d < m.D; ++d) sm = __fadd_rn(sm, exp_ex2(__fsub_rn(hb[(size_t)d * m.P + p], mx)));
+      }
+      for (int r = 0; r < cnt; ++r) {
+        const int rdv = rd_in[((size_t)fb * m.D + r) * kBP + t];
+        const int vox = vox_in[((size_t)fb * m.D + r) * kBP + t];
+        const int d0 = rdv & kDMask, d1 = (rdv >> 9) & kDMask;
+        float wgt = 0.0f;
+        for (int d = d0; d < d1; ++d) {
+          const float x = hb[(size_t)d * m.P + p];
+          wgt = __fadd_rn(wgt, m.logits ? exp_ex2(__fsub_rn(x, mx)) : x);
+        }
+        if (m.logits) wgt = __fmul_rn(wgt, __fdiv_rn(1.0f, sm));
+        for (int c = lane; c < m.C; c += 32) {
+          float x = c < Cc ? to_f32<CT>(cb[(size_t)c * m.P + p]) : semp[min(c - Cc, 15)];
+          atomicAdd(bevb + (size_t)c * m.V + vox, __fmul_rn(wgt, x));
+        }
+      }
+    }
   }
 }
 
@@ -538,8 +596,8 @@ constexpr int kCombList = 1024;   // contributing blocks kept in shared memory p
 
 template <int NV>
 __global__ void __launch_bounds__(kCombThreads)
-bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const unsigned *__restrict__ fmask,
-                  const unsigned *__restrict__ fbase, const float *__restrict__ prow, float *__restrict__ bev) {
+bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const uint2 *__restrict__ ftab,
+                  const float *__restrict__ prow, float *__restrict__ bev) {
   constexpr int kCpad = 32 * NV;
   __shared__ unsigned l_mask[kCombList];
   __shared__ int l_row[kCombList];
@@ -550,7 +608,7 @@ bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const unsigned *_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = tid >> 3, l = tid & 7;   // voxel of the strip, lane of its group
   const unsigned below = (1u << g) - 1u;
-  const float *pr = prow + (size_t)b * m.rows_cap * kCpad;
+  const float *pr = prow + (size_t)b * m.rows_cap * kCpad + 4 * l;
   float acc[NV][4];
 #pragma unroll
   for (int k = 0; k < NV; ++k)
@@ -566,12 +624,10 @@ bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const unsigned *_
     int row = 0;
     if (kb < m.NB) {
       const size_t fbk = (size_t)b * m.NB + kb;
-      mk = fmask[fbk * m.nstrips + strip];
-      if (mk) {
-        const int rb = info[fbk].row_base;
-        if (rb < 0) mk = 0u;   // completed by the fix-up launch
-        else row = rb + (int)fbase[fbk * m.nstrips + strip];
-      }
+      const uint2 e = __ldg(ftab + fbk * m.nstrips + strip);   // {mask, slot of the strip's first touched voxel}
+      const int rb = __ldg(&info[fbk].row_base);
+      mk = rb < 0 ? 0u : e.x;   // rb < 0: completed by the fix-up launch
+      row = rb + (int)e.y;
     }
     // ordered compaction of the contributing blocks among kb0 .. kb0 + 255
     const unsigned bal = __ballot_sync(0xffffffffu, mk != 0u);
@@ -592,7 +648,7 @@ bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const unsigned *_
       for (int i = 0; i < total; ++i) {
         const unsigned mk_i = l_mask[i];
         if ((mk_i >> g) & 1u) {
-          const float *src = pr + (size_t)(l_row[i] + __popc(mk_i & below)) * kCpad + 4 * l;
+          const float *src = pr + (size_t)(l_row[i] + __popc(mk_i & below)) * kCpad;
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const float4 x = __ldg(reinterpret_cast<const float4 *>(src + 32 * k));
@@ -610,7 +666,7 @@ bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const unsigned *_
 #pragma unroll
   for (int k = 0; k < NV; ++k)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) tile[chan_of(k, l, e) * 33 + g] = acc[k][e];
+    for (int e = 0; e < 4; ++e) tile[(32 * k + 4 * l + e) * 33 + g] = acc[k][e];
   __syncthreads();
   const int v = strip * 32 + lane;
   if (v < m.V) {
@@ -620,106 +676,117 @@ bp_combine_kernel(BDims m, const BlockInfo *__restrict__ info, const unsigned *_
 }
 
 // ---------------------------------------------------------------------------------------------
-// BACKWARD.  grid (NB, B), 512 threads, dynamic smem: col [D][64] | tile [Cpad][65] | G [cap][Cpad] | strip list
+// BACKWARD.  grid (NB, B), 512 threads, dynamic smem:
+//   col [D][64] | tile [Cpad][65] | G [cap][Cpad] | svox [cap] | rd_s [kRunsStaged][64] | gw_s [kRunsStaged][64]
 // ---------------------------------------------------------------------------------------------
+constexpr int kRunsStaged = 32;   // run descriptors / run gradients of a pixel kept in shared memory; the rest in HBM
+
 template <typename CT, int NV>
 __global__ void __launch_bounds__(kFwdThreads, 2)
 bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16, const CT *__restrict__ context,
                    const float *__restrict__ grad_bev, const int *__restrict__ cnt_in,
                    const int *__restrict__ rd_in, const BlockInfo *__restrict__ info,
-                   const unsigned *__restrict__ fmask, const unsigned *__restrict__ fbase,
-                   float *__restrict__ gw_ws, float *__restrict__ g_height, float *__restrict__ g_context) {
+                   const uint2 *__restrict__ ftab, float *__restrict__ gw_ws, float *__restrict__ g_height,
+                   float *__restrict__ g_context) {
   constexpr int kCpad = 32 * NV;
   constexpr int kLd = kBP + 1;
   extern __shared__ __align__(16) float bsm_[];
-  __shared__ int s_nlist;
   const int b = blockIdx.y, kb = blockIdx.x;
   const size_t fbk = (size_t)b * m.NB + kb;
   const BlockInfo bi = info[fbk];
   float *col = bsm_;
   float *tile = col + m.D * kBP;                 // [Cpad][65]: context in, g_ctx out
   float *G = tile + kCpad * kLd;                 // [cap][Cpad], chunks XOR-swizzled by the slot
-  int *list = reinterpret_cast<int *>(G + (size_t)cap * kCpad);   // [cap + 1][3]: strip, mask, slot base
+  int *svox = reinterpret_cast<int *>(G + (size_t)cap * kCpad);   // [cap] voxel of the round's slots
+  int *rd_s = svox + cap;                        // [kRunsStaged][64]
+  float *gw_s = reinterpret_cast<float *>(rd_s + kRunsStaged * kBP);   // [kRunsStaged][64]
   const int n = kb / m.nblk, blk = kb - n * m.nblk;
   const int bn = b * m.Nc + n;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t = tid >> 3, l = tid & 7;
   const unsigned gmask = 0xffu << (lane & 24);
   const int glane0 = lane & 24;
+  const Org o = block_origin(m, blk);
 
-  // ---- stage ----------------------------------------------------------------------------------------
-  stage_block_columns(col, height + (size_t)bn * m.hs, m, blk, vec16 != 0);
+  // ---- stage (all asynchronous) ------------------------------------------------------------------------
+  stage_block_columns(col, height + (size_t)bn * m.hs, m, o, vec16 != 0);
+  {
+    const int nst = min(bi.max_runs, kRunsStaged);
+    const int *rsrc = rd_in + fbk * m.D * kBP;
+    for (int i = tid; i < nst * (kBP / 4); i += kFwdThreads)
+      cp_async_16(reinterpret_cast<float *>(rd_s) + 4 * i, reinterpret_cast<const float *>(rsrc) + 4 * i);
+  }
+  cp_async_commit();
   {
     const CT *cb = context + (size_t)bn * m.cs;
-    for (int i = tid; i < m.C * kBP; i += kFwdThreads) {
-      const int c = i >> 6, tp = i & 63;
-      const Pix q = pixel_of(m, blk, tp);
-      if (q.valid) {
-        if (sizeof(CT) == 4) cp_async_4(tile + c * kLd + tp, reinterpret_cast<const float *>(cb) + (size_t)c * m.P + q.p);
-        else tile[c * kLd + tp] = ld_ctx<CT>(cb + (size_t)c * m.P + q.p);
-      } else {
-        tile[c * kLd + tp] = 0.0f;
-      }
+    const int tp = tid & 63;
+    const int r = tp >> 3, cc = tp & 7;
+    const bool ok = o.h0 + r < m.fH && o.w0 + cc < m.fW;
+    const int off = (o.h0 + r) * m.fW + o.w0 + cc;
+    for (int c = tid >> 6; c < m.C; c += kFwdThreads >> 6) {
+      if (sizeof(CT) == 4) cp_async_4_zfill(tile + c * kLd + tp, reinterpret_cast<const float *>(cb) + (ok ? c * m.P + off : 0), ok);
+      else tile[c * kLd + tp] = ok ? to_f32<CT>(cb[c * m.P + off]) : 0.0f;
     }
   }
-  cp_async_wait_all();
-  __syncthreads();
-
+  cp_async_commit();
   const int cnt = cnt_in[fbk * kBP + t];
+  const int *rdp = rd_in + fbk * m.D * kBP + t;
+  float *gwp = gw_ws + fbk * m.D * kBP + t;
+  const uint2 *ft = ftab + fbk * m.nstrips;
+  const float *gb = grad_bev + (size_t)b * m.C * m.V;
+  cp_async_wait_group<1>();   // columns + run descriptors
+  __syncthreads();
   float scale = 1.0f;
   if (m.logits) scale = softmax_block_column(col, m.D, t, l, gmask);
+  cp_async_wait_group<0>();   // context
+  __syncthreads();
   float cx[NV][4], acc[NV][4];
 #pragma unroll
   for (int k = 0; k < NV; ++k)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int c = chan_of(k, l, e);
+      const int c = 32 * k + 4 * l + e;
       cx[k][e] = c < m.C ? tile[c * kLd + t] : 0.0f;
       acc[k][e] = 0.0f;
     }
-  const int *rdp = rd_in + fbk * m.D * kBP;
-  float *gwp = gw_ws + fbk * m.D * kBP;
-  const unsigned *gm = fmask + fbk * m.nstrips, *gbs = fbase + fbk * m.nstrips;
-  const float *gb = grad_bev + (size_t)b * m.C * m.V;
   float S = 0.0f;
+  auto load_rd = [&](int r) -> int { return r < kRunsStaged ? rd_s[r * kBP + t] : rdp[r * kBP]; };
 
   for (int lo = 0; lo < bi.nslots; lo += cap) {
     const int nr = min(cap, bi.nslots - lo);
-    if (tid == 0) s_nlist = 0;
-    __syncthreads();   // (also: the previous round's reads of G are done)
-    // strips of the footprint that hold a slot of this round (order irrelevant: each row is written once)
+    __syncthreads();   // the previous round's reads of G / svox are done
+    // voxel of every slot of this round: expand the footprint bitmap (strips whose slots overlap [lo, lo + nr))
     for (int i = tid; i < m.nstrips; i += kFwdThreads) {
-      const unsigned mk = gm[i];
-      if (mk) {
-        const int sb = (int)gbs[i];
-        if (sb < lo + nr && sb + __popc(mk) > lo) {
-          const int at = atomicAdd(&s_nlist, 1);
-          list[3 * at] = i; list[3 * at + 1] = (int)mk; list[3 * at + 2] = sb;
+      const uint2 e = __ldg(ft + i);
+      if (e.x) {
+        int s = (int)e.y - lo;
+        if (s < nr && s + __popc(e.x) > 0) {
+          unsigned bits = e.x;
+          while (bits) {
+            const int vt = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if ((unsigned)s < (unsigned)nr) svox[s] = i * 32 + vt;
+            ++s;
+          }
         }
       }
     }
     __syncthreads();
-    const int nlist = s_nlist;
-    // gradient rows of those voxels: lane <-> voxel of the strip, 128-byte line per channel and strip
-    for (int i = wid; i < nlist; i += kFwdThreads / 32) {
-      const int strip = list[3 * i];
-      const unsigned mk = (unsigned)list[3 * i + 1];
-      const int s = list[3 * i + 2] + __popc(mk & ((1u << lane) - 1u)) - lo;
-      const int v = strip * 32 + lane;
-      const bool on = ((mk >> lane) & 1u) && (unsigned)s < (unsigned)nr;
-      const float *src = gb + v;
+    // gradient rows of those voxels, straight from the NCHW gradient: lane <-> slot (consecutive slots are mostly
+    // consecutive voxels: x-runs), four channel planes per 16-byte chunk, 16 loads in flight
+    for (int s0 = wid * 32; s0 < nr; s0 += kFwdThreads) {
+      const int s = s0 + lane;
+      const bool on = s < nr;
+      const float *src = gb + (on ? svox[s] : 0);
       float *dst = G + (size_t)s * kCpad;
+      for (int j0 = 0; j0 < kCpad; j0 += 16) {   // (pad channels are written as zeros: they meet cx = 0 in the dot product)
+        float x[16];
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-#pragma unroll 2
-        for (int lp = 0; lp < 8; ++lp) {
-          float e[4];
+        for (int u = 0; u < 16; ++u) x[u] = (on && j0 + u < m.C) ? __ldg(src + (size_t)(j0 + u) * m.V) : 0.0f;
+        if (on) {
 #pragma unroll
-          for (int ee = 0; ee < 4; ++ee) {
-            const int c = chan_of(k, lp, ee);
-            e[ee] = (on && c < m.C) ? __ldg(src + (size_t)c * m.V) : 0.0f;
-          }
-          if (on) *reinterpret_cast<float4 *>(dst + 4 * row_chunk(s, k, lp)) = make_float4(e[0], e[1], e[2], e[3]);
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4 *>(dst + 4 * swz((j0 >> 2) + q, s)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
         }
       }
     }
@@ -730,10 +797,8 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
       float my_w = 0.0f, my_gw = 0.0f;
       const bool mine = r0 + l < cnt;
       if (mine) {
-        my_rd = rdp[(r0 + l) * kBP + t];
-        const int d0 = my_rd & kDMask, d1 = (my_rd >> 9) & kDMask;
-        float w = 0.0f;
-        for (int d = d0; d < d1; ++d) w = __fadd_rn(w, col[d * kBP + t]);
+        my_rd = load_rd(r0 + l);
+        const float w = run_weight(col, t, my_rd);
         my_w = m.logits ? __fmul_rn(w, scale) : w;
       }
       const int nj = min(8, cnt - r0);
@@ -742,11 +807,11 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
         const float wj = __shfl_sync(gmask, my_w, glane0 + j);
         const int s = (int)((unsigned)rdj >> kSlotShift) - lo;
         if ((unsigned)s < (unsigned)nr) {
-          const float *grow = G + (size_t)s * kCpad;
+          const float *grow = G + (size_t)s * kCpad + 4 * ((l ^ s) & 7);
           float da = 0.0f, db = 0.0f;
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
-            const float4 x = *reinterpret_cast<const float4 *>(grow + 4 * row_chunk(s, k, l));
+            const float4 x = *reinterpret_cast<const float4 *>(grow + 32 * k);
             fma2(acc[k][0], acc[k][1], wj, x.x, x.y);
             fma2(acc[k][2], acc[k][3], wj, x.z, x.w);
             da = __fmaf_rn(cx[k][0], x.x, da); db = __fmaf_rn(cx[k][1], x.y, db);
@@ -762,7 +827,10 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
       }
       if (mine) {
         const int s = (int)((unsigned)my_rd >> kSlotShift) - lo;
-        if ((unsigned)s < (unsigned)nr) gwp[(r0 + l) * kBP + t] = my_gw;
+        if ((unsigned)s < (unsigned)nr) {
+          if (r0 + l < kRunsStaged) gw_s[(r0 + l) * kBP + t] = my_gw;
+          else gwp[(r0 + l) * kBP] = my_gw;
+        }
       }
     }
   }
@@ -773,20 +841,21 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
   for (int k = 0; k < NV; ++k)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int c = chan_of(k, l, e);
+      const int c = 32 * k + 4 * l + e;
       if (c < m.C) tile[c * kLd + t] = acc[k][e];
     }
   {
     // lane l owns the bins d = l mod 8; every lane walks the pixel's runs in order
     int dc = l;
+    float *cp = col + t;
     auto put = [&](int d, float gv) {
       float v = gv;
-      if (m.logits) v = __fmul_rn(__fmul_rn(col[d * kBP + t], scale), __fsub_rn(gv, S));
-      col[d * kBP + t] = v;
+      if (m.logits) v = __fmul_rn(__fmul_rn(cp[d * kBP], scale), __fsub_rn(gv, S));
+      cp[d * kBP] = v;
     };
     for (int r = 0; r < cnt; ++r) {
-      const int rdv = rdp[r * kBP + t];
-      const float gv = gwp[r * kBP + t];
+      const int rdv = load_rd(r);
+      const float gv = r < kRunsStaged ? gw_s[r * kBP + t] : gwp[r * kBP];
       const int d0 = rdv & kDMask, d1 = (rdv >> 9) & kDMask;
       for (; dc < d0; dc += 8) put(dc, 0.0f);
       for (; dc < d1; dc += 8) put(dc, gv);
@@ -796,29 +865,25 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
   __syncthreads();
   // ---- coalesced stores --------------------------------------------------------------------------------
   {
-    const int bi_ = blk / m.nbw, bj_ = blk - bi_ * m.nbw;
-    const int h0 = bi_ * 8, w0 = bj_ * 8;
-    float *gh = g_height + (size_t)bn * m.ghs;
-    float *gc = g_context + (size_t)bn * m.gcs;
-    const bool full = h0 + 8 <= m.fH && w0 + 8 <= m.fW;
-    const bool v16h = full && (m.fW % 4 == 0) && (m.ghs % 4 == 0) && (reinterpret_cast<uintptr_t>(g_height) % 16 == 0);
+    float *gh = g_height + (size_t)bn * m.ghs + o.h0 * m.fW + o.w0;
+    float *gc = g_context + (size_t)bn * m.gcs + o.h0 * m.fW + o.w0;
+    const bool v16h = o.full && (m.fW % 4 == 0) && (m.ghs % 4 == 0) && (reinterpret_cast<uintptr_t>(g_height) % 16 == 0);
     if (v16h) {
-      for (int i = tid; i < m.D * 16; i += kFwdThreads) {
-        const int d = i >> 4, row = (i >> 1) & 7, half = i & 1;
-        const float4 v = *reinterpret_cast<const float4 *>(col + d * kBP + row * 8 + half * 4);
-        stg_stream_f4(reinterpret_cast<float4 *>(gh + (size_t)d * m.P + (size_t)(h0 + row) * m.fW + w0 + half * 4), v);
-      }
+      const int row = (tid >> 1) & 7, half = tid & 1;
+      const int off = row * m.fW + half * 4, soff = row * 8 + half * 4;
+      for (int d = tid >> 4; d < m.D; d += kFwdThreads >> 4)
+        stg_stream_f4(reinterpret_cast<float4 *>(gh + (size_t)d * m.P + off), *reinterpret_cast<const float4 *>(col + d * kBP + soff));
     } else {
-      for (int i = tid; i < m.D * kBP; i += kFwdThreads) {
-        const int d = i >> 6, tp = i & 63;
-        const int h = h0 + (tp >> 3), w = w0 + (tp & 7);
-        if (h < m.fH && w < m.fW) stg_stream_f1(gh + (size_t)d * m.P + (size_t)h * m.fW + w, col[i]);
-      }
+      const int tp = tid & 63;
+      const int r = tp >> 3, cc = tp & 7;
+      if (o.h0 + r < m.fH && o.w0 + cc < m.fW)
+        for (int d = tid >> 6; d < m.D; d += kFwdThreads >> 6) stg_stream_f1(gh + (size_t)d * m.P + r * m.fW + cc, col[d * kBP + tp]);
     }
-    for (int i = tid; i < m.C * kBP; i += kFwdThreads) {
-      const int c = i >> 6, tp = i & 63;
-      const int h = h0 + (tp >> 3), w = w0 + (tp & 7);
-      if (h < m.fH && w < m.fW) stg_stream_f1(gc + (size_t)c * m.P + (size_t)h * m.fW + w, tile[c * kLd + tp]);
+    {
+      const int tp = tid & 63;
+      const int r = tp >> 3, cc = tp & 7;
+      if (o.h0 + r < m.fH && o.w0 + cc < m.fW)
+        for (int c = tid >> 6; c < m.C; c += kFwdThreads >> 6) stg_stream_f1(gc + (size_t)c * m.P + r * m.fW + cc, tile[c * kLd + tp]);
     }
   }
 }
@@ -854,12 +919,14 @@ size_t smem_budget() { return 111 * 1024; }
 int forward_cap(const BDims &m, int Cs) {
   const size_t fixed = sizeof(float) * ((size_t)m.D * kBP + (size_t)kBP * m.Cpad + (size_t)Cs * kBP);
   const long long left = (long long)smem_budget() - (long long)fixed;
-  return (int)std::max<long long>(left / (kBP * 4 + 8), 0);
+  return (int)std::max<long long>(left / (kBP * 4 + 8), 0) & ~3;
+}
+size_t backward_fixed_smem(const BDims &m) {
+  return sizeof(float) * ((size_t)m.D * kBP + (size_t)m.Cpad * (kBP + 1)) + 2 * sizeof(float) * kRunsStaged * kBP + 16;
 }
 int backward_cap(const BDims &m) {
-  const size_t fixed = sizeof(float) * ((size_t)m.D * kBP + (size_t)m.Cpad * (kBP + 1)) + 16;
-  const long long left = (long long)smem_budget() - (long long)fixed;
-  return (int)std::max<long long>(left / (m.Cpad * 4 + 12) - 1, 0);
+  const long long left = (long long)smem_budget() - (long long)backward_fixed_smem(m);
+  return (int)std::max<long long>(left / (m.Cpad * 4 + 4), 0) & ~3;
 }
 
 template <typename CT, int NV>
@@ -871,15 +938,14 @@ int launch_forward(const BDims &m, const BWorkspace &w, const float *height, con
                       8 * (size_t)cap;
   const int vec16 = columns_vec16(height, m.hs, m.P) && (m.fW % 4 == 0);
   dim3 grid(m.NB, m.B);
-  if (int rc = set_smem(bp_forward_kernel<CT, NV, false>, smem)) return rc;
-  bp_forward_kernel<CT, NV, false><<<grid, kFwdThreads, smem, s>>>(
-      m, cap, height, vec16, static_cast<const CT *>(context), bsm, w.cnt, w.rd, w.vox, w.info, w.alloc, w.prow, bev);
+  if (int rc = set_smem(bp_forward_kernel<CT, NV>, smem)) return rc;
+  bp_forward_kernel<CT, NV><<<grid, kFwdThreads, smem, s>>>(m, cap, height, vec16, static_cast<const CT *>(context), bsm,
+                                                           w.cnt, w.rd, w.info, w.prow);
   SGV3D_CHECK_LAUNCH("bp_forward_kernel");
-  bp_combine_kernel<NV><<<dim3(m.nstrips, m.B), kCombThreads, 0, s>>>(m, w.info, w.fmask, w.fbase, w.prow, bev);
+  bp_combine_kernel<NV><<<dim3(m.nstrips, m.B), kCombThreads, 0, s>>>(m, w.info, w.ftab, w.prow, bev);
   SGV3D_CHECK_LAUNCH("bp_combine_kernel");
-  if (int rc = set_smem(bp_forward_kernel<CT, NV, true>, smem)) return rc;
-  bp_forward_kernel<CT, NV, true><<<grid, kFwdThreads, smem, s>>>(
-      m, cap, height, vec16, static_cast<const CT *>(context), bsm, w.cnt, w.rd, w.vox, w.info, w.alloc, w.prow, bev);
+  bp_fixup_kernel<CT><<<std::min(m.B * m.NB, 2 * kNumSMs), 256, 0, s>>>(m, height, static_cast<const CT *>(context), bsm, w.cnt,
+                                                                     w.rd, w.vox, w.info, w.alloc, bev);
   SGV3D_CHECK_LAUNCH("bp_fixup_kernel");
   return SGV3D_OK;
 }
@@ -898,13 +964,12 @@ template <typename CT, int NV>
 int launch_backward(const BDims &m, const BWorkspace &w, const float *grad_bev, const float *height,
                     const void *context, float *g_height, float *g_context, cudaStream_t s) {
   const int cap = std::min(backward_cap(m), 4096);
-  const size_t smem = sizeof(float) * ((size_t)m.D * kBP + (size_t)m.Cpad * (kBP + 1) + (size_t)cap * m.Cpad) +
-                      12 * (size_t)(cap + 1);
+  const size_t smem = backward_fixed_smem(m) + (size_t)cap * (m.Cpad * 4 + 4);
   const int vec16 = columns_vec16(height, m.hs, m.P) && (m.fW % 4 == 0);
   if (int rc = set_smem(bp_backward_kernel<CT, NV>, smem)) return rc;
   bp_backward_kernel<CT, NV><<<dim3(m.NB, m.B), kFwdThreads, smem, s>>>(
-      m, cap, height, vec16, static_cast<const CT *>(context), grad_bev, w.cnt, w.rd, w.info, w.fmask, w.fbase, w.gw,
-      g_height, g_context);
+      m, cap, height, vec16, static_cast<const CT *>(context), grad_bev, w.cnt, w.rd, w.info, w.ftab, w.gw, g_height,
+      g_context);
   SGV3D_CHECK_LAUNCH("bp_backward_kernel");
   return SGV3D_OK;
 }
@@ -943,7 +1008,7 @@ int plan(const Dims &d, int arith, const float *u_tab, const float *v_tab, const
   do {                                                                                                           \
     if (int rc = set_smem(bp_plan_kernel<A>, smem)) return rc;                                                   \
     bp_plan_kernel<A><<<g, kBP, smem, s>>>(m, u_tab, v_tab, z_tab, ida_inv, m_virtual, m_ego, bda, ref_heights,  \
-                                           grid, w.cnt, w.vox, w.rd, w.info, w.fmask, w.fbase, w.alloc);         \
+                                           grid, w.cnt, w.vox, w.rd, w.info, w.ftab, w.alloc);                 \
   } while (0)
   if (arith == SGV3D_ARITH_PAIR) SGV3D_BP_PLAN(SGV3D_ARITH_PAIR);
   else if (arith == SGV3D_ARITH_FMA) SGV3D_BP_PLAN(SGV3D_ARITH_FMA);

@@ -47,8 +47,8 @@ _DEFAULT_PIPELINE = PIPELINE_AUTO
 
 
 def set_default_pipeline(pipeline: int) -> None:
-    """Which kernels serve new plans: AUTO (the pixel-block pipeline whenever it supports the shape -- rows of up to
-    96 channels, D <= 255 -- else the voxel-tile pipeline), TILE or BLOCK (forced; tests compare the two)."""
+    """Which kernels serve new plans: AUTO (= the voxel-tile pipeline, the faster one on B200 for every reference
+    shape), TILE, or BLOCK (the pixel-block pipeline: rows of up to 96 channels, D <= 255; error otherwise)."""
     global _DEFAULT_PIPELINE
     assert pipeline in (PIPELINE_AUTO, PIPELINE_TILE, PIPELINE_BLOCK)
     _DEFAULT_PIPELINE = pipeline

@@ -12,12 +12,28 @@ from tests.helpers import frustum_axes, kept_mask_np, oracle_frustum
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tile", "auto"])
-def pipeline(request):
-    """Every test of this file runs on both kernel pipelines: "tile" = voxel-tile (global sort by voxel + row gathers),
-    "auto" = the pixel-block pipeline wherever it supports the shape (C <= 96, D <= 255), else voxel-tile."""
+class _BlockWhereSupported(int):
+    """pipeline selector resolved per plan: BLOCK when the shape is supported (C <= 96, D <= 255), else TILE"""
+
+
+@pytest.fixture(autouse=True, params=["tile", "block"])
+def pipeline(request, monkeypatch):
+    """Every test of this file runs on both kernel pipelines: "tile" = voxel-tile (global sort by voxel + row gathers;
+    the default), "block" = the pixel-block pipeline wherever it supports the shape, else voxel-tile."""
     from sgv3d_b200 import view_transform as VT
-    VT.set_default_pipeline(VT.PIPELINE_TILE if request.param == "tile" else VT.PIPELINE_AUTO)
+    if request.param == "tile":
+        VT.set_default_pipeline(VT.PIPELINE_TILE)
+    else:
+        VT.set_default_pipeline(VT.PIPELINE_BLOCK)
+        orig = VT.LiftSplatPlan.__init__
+
+        def init(self, frustum, *a, **kw):
+            ch = a[9] if len(a) > 9 else kw.get("channels")
+            d = int(frustum.shape[0])
+            if ch is None or ch > 96 or d > 255:      # not supported by the pixel-block pipeline
+                kw["pipeline"] = VT.PIPELINE_TILE
+            return orig(self, frustum, *a, **kw)
+        monkeypatch.setattr(VT.LiftSplatPlan, "__init__", init)
     yield request.param
     VT.set_default_pipeline(VT.PIPELINE_AUTO)
 
