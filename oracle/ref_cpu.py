@@ -25,7 +25,7 @@ import types
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PYC = os.path.join(_HERE, "_ref", "ref_lss_fpn.pyc")
+PYC = os.path.join(_HERE, "_ref", "ref_lss_fpn.pycode")
 
 _lss = None
 
@@ -49,7 +49,7 @@ def load():
     if _lss is not None:
         return _lss
     if not available():
-        raise RuntimeError("oracle/_ref/ref_lss_fpn.pyc missing: run `make -C oracle ref` where /root/reference exists")
+        raise RuntimeError("oracle/_ref/ref_lss_fpn.pycode missing: run `make -C oracle ref` where /root/reference exists")
     _stub("mmcv"); _stub("mmcv.cnn", build_conv_layer=None)
     _stub("mmdet3d"); _stub("mmdet3d.models", build_neck=None)
     _stub("mmdet"); _stub("mmdet.models", build_backbone=None)
