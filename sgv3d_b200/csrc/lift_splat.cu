@@ -1328,8 +1328,8 @@ constexpr int kBwdLd = kBwdPix + 1;
 
 template <typename CT, int NV, int OCC>
 __global__ void __launch_bounds__(kBwdPix * 4, OCC)
-ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__restrict__ context,
-                         const float *__restrict__ gT, const int *__restrict__ run_cnt,
+ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, int vec16_out,
+                         const CT *__restrict__ context, const float *__restrict__ gT, const int *__restrict__ run_cnt,
                          const int *__restrict__ run_vox, const int *__restrict__ run_d,
                          float *__restrict__ w_pm, float *__restrict__ gw_pm, float *__restrict__ g_height,
                          float *__restrict__ g_context) {
@@ -1351,9 +1351,16 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__r
   // ---- 1. stage ------------------------------------------------------------------------------------
   {
     const int t = tid & (kBwdPix - 1), q = tid >> 6;  // 4 quarter-blocks of threads, each walks a share of the rows
-    if (t < npx) {
+    if (vec16 && npx == kBwdPix) {
+      // 16 lanes copy one 256-byte row of the height block per instruction
+      const int t4 = tid & 15;
+      const float *hs = height + (size_t)bn * m.hs + p0 + 4 * t4;
+      for (int d = tid >> 4; d < m.D; d += (kBwdPix * 4) >> 4) cp_async_16(col + d * kBwdPix + 4 * t4, hs + (size_t)d * m.P);
+    } else if (t < npx) {
       const float *hs = height + (size_t)bn * m.hs + p0 + t;
       for (int d = q; d < m.D; d += 4) cp_async_4(col + d * kBwdPix + t, hs + (size_t)d * m.P);
+    }
+    if (t < npx) {
       const CT *cs = context + (size_t)bn * m.cs + p0 + t;
       if (sizeof(CT) == 4) {
         for (int c = q; c < m.C; c += 4)
@@ -1478,13 +1485,14 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__r
   }
   __syncthreads();  // tile complete; gw_pm writes of this CTA are visible to it
 
-  // ---- 4a. g_height: lane l writes the bins d = l mod 4 ------------------------------------------------
+  // ---- 4a. g_height: lane l computes the bins d = l mod 4 in place of the staged column, then the block leaves as
+  //          whole 256-byte rows (128-bit stores) ----------------------------------------------------------------
   if (live) {
-    float *gh = g_height + (size_t)bn * m.ghs + p0 + px;
+    float *cp = col + px;
     auto put = [&](int d, float gv) {
       float v = gv;
-      if (m.logits) v = __fmul_rn(__fmul_rn(col[d * kBwdPix + px], scale), __fsub_rn(gv, S));
-      stg_stream_f1(gh + (size_t)d * m.P, v);
+      if (m.logits) v = __fmul_rn(__fmul_rn(cp[d * kBwdPix], scale), __fsub_rn(gv, S));
+      cp[d * kBwdPix] = v;
     };
     int dc = l;  // next bin of this lane
     for (int r = 0; r < cnt; ++r) {
@@ -1496,6 +1504,19 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, const CT *__r
       for (; dc < d1; dc += 4) put(dc, gv);
     }
     for (; dc < m.D; dc += 4) put(dc, 0.0f);
+  }
+  __syncthreads();
+  if (vec16_out && npx == kBwdPix) {
+    const int t4 = tid & 15;
+    float *gh = g_height + (size_t)bn * m.ghs + p0 + 4 * t4;
+    for (int d = tid >> 4; d < m.D; d += (kBwdPix * 4) >> 4)
+      stg_stream_f4(reinterpret_cast<float4 *>(gh + (size_t)d * m.P), *reinterpret_cast<const float4 *>(col + d * kBwdPix + 4 * t4));
+  } else {
+    const int t = tid & (kBwdPix - 1), q = tid >> 6;
+    if (t < npx) {
+      float *gh = g_height + (size_t)bn * m.ghs + p0 + t;
+      for (int d = q; d < m.D; d += 4) stg_stream_f1(gh + (size_t)d * m.P, col[d * kBwdPix + t]);
+    }
   }
   // ---- 4b. g_ctx tile -> NCHW rows (256-byte segments) ------------------------------------------------
   {
@@ -1626,14 +1647,16 @@ int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *he
   // CTAs per SM: the kernel is latency bound (dependent gather -> FMA -> shuffle chains), so a third resident CTA pays
   // for the ~14 words of spill it costs at <= 80 channels (DAIR-R50: 440 -> 385 us at 64 frames); with 96-float rows
   // the spills dominate (SGV3D-BSM-R50: 737 -> 1117 us), so those keep two.  SGV3D_BWD_OCC overrides (experiments).
+  const int vec16 = columns_vec16(height, m.hs, m.P) ? 1 : 0;
+  const int vec16_out = columns_vec16(grad_height, m.ghs, m.P) ? 1 : 0;
   static const int occ_env = getenv("SGV3D_BWD_OCC") ? atoi(getenv("SGV3D_BWD_OCC")) : 0;
   const int occ = occ_env ? occ_env : (NV <= 3 ? 4 : (NV <= 5 ? 3 : 2));
 #define SGV3D_BWD_CHUNK(OCC)                                                                                   \
   do {                                                                                                         \
     if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC>, smem)) return rc;                             \
     ls_backward_chunk_kernel<CT, NV, OCC><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(                 \
-        m, height, static_cast<const CT *>(context), w.gT, w.run_cnt, w.run_vox, w.run_d, w.w_pm, w.gw_pm,     \
-        grad_height, grad_context);                                                                            \
+        m, height, vec16, vec16_out, static_cast<const CT *>(context), w.gT, w.run_cnt, w.run_vox, w.run_d,    \
+        w.w_pm, w.gw_pm, grad_height, grad_context);                                                           \
   } while (0)
   if (occ >= 4) SGV3D_BWD_CHUNK(4);
   else if (occ == 3) SGV3D_BWD_CHUNK(3);
