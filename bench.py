@@ -52,6 +52,8 @@ def _ncu_traffic(kernels, shape_name, frames):
     t = json.load(open(p))
     if t.get("shape") != shape_name or t.get("frames_per_launch") != frames:
         return None
+    if kernels is None:          # every kernel of the captured training step (plan + forward + backward)
+        return sum(t["dram_bytes_per_launch"].values())
     tot = 0
     for base in sorted({k.split("(")[0] for k in kernels}):   # the two prep roles were captured as one launch
         if base not in t["dram_bytes_per_launch"]:
@@ -364,17 +366,20 @@ def run_ours(args):
     from sgv3d_b200.view_transform import LiftSplatPlan  # noqa: F401
     D_, C_ = shape.D, shape.channels
     train_sets = []
+    ctx_dt = torch.bfloat16 if args.ctx == "bf16" else torch.float32
     for hf, md, _ in sets:
-        plan = mod.make_plan(md, 0, C_)
+        plan = mod.make_plan(md, 0, C_, ctx_dt)
         gb = torch.randn(B, C_, shape.grid[1], shape.grid[0], device=dev)
         gout = torch.empty_like(hf)
-        train_sets.append((plan, hf, gb, gout))
+        # BASELINE config 4: bf16 context (a separate tensor: the height logits stay fp32), fp32 accumulation and gradients
+        cx = hf[:, D_:D_ + C_].to(ctx_dt).contiguous() if ctx_dt != torch.float32 else hf[:, D_:D_ + C_]
+        train_sets.append((plan, hf, gb, gout, cx))
 
     def train_step(i):
-        plan, hf, gb, gout = train_sets[i % nsets]
+        plan, hf, gb, gout, cx = train_sets[i % nsets]
         plan.rebuild()
-        plan.forward(hf[:, :D_], hf[:, D_:D_ + C_], logits=True)
-        plan.backward(gb, hf[:, :D_], hf[:, D_:D_ + C_], logits=True, out_height=gout[:, :D_], out_context=gout[:, D_:D_ + C_])
+        plan.forward(hf[:, :D_], cx, logits=True)
+        plan.backward(gb, hf[:, :D_], cx, logits=True, out_height=gout[:, :D_], out_context=gout[:, D_:D_ + C_])
 
     for i in range(W):
         train_step(i)
@@ -448,8 +453,11 @@ def run_ours(args):
     e2e_value = frames_total / (ms_e2e * 1e-3)
 
     extra = {}
-    if rank == 0 and not args.quick:
-        extra = extra_measurements(args, shape, mod, sets, dev)
+    if not args.quick:
+        shapes = shape_lines(args, dev, world, barrier)     # every rank takes part (sharded like the headline)
+        if rank == 0:
+            extra = extra_measurements(args, shape, mod, sets, dev)
+            extra["shapes"] = shapes
 
     if rank != 0:
         if world > 1:
@@ -459,7 +467,9 @@ def run_ours(args):
 
     peak, peak_src = _peaks()
     fwd_bytes = shape.fused_forward_bytes() * B           # 8.77 MB/frame at DAIR-R50
-    train_bytes = fwd_bytes + shape.fused_backward_bytes() * B   # + 12.29 MB/frame = 21.06 MB/frame
+    cb = 2 if args.ctx == "bf16" else 4
+    # + 12.29 MB/frame = 21.06 MB/frame with fp32 context (19.40 MB with bf16 context, fp32 grad_ctx)
+    train_bytes = shape.fused_forward_bytes(cb) * B + shape.fused_backward_bytes(cb) * B
     # forward-only step: ONE CUDA-graph launch (4x4 prep + plan + forward); its duration is the device-timed contract
     # window above.  Training step: plan + forward + backward, timed the same way (CUDA events on the launch stream).
     step_ms = ms / K
@@ -471,17 +481,18 @@ def run_ours(args):
     # roofline; the forward-only (inference) step is reported beside it
     roofline = {
         "bound": "hbm", "achieved": train_achieved, "peak": peak, "unit": "GB/s", "frac": train_achieved / peak,
-        "traffic": _ncu_traffic(list(kern.keys()), shape.name, B),
+        "traffic": _ncu_traffic(None, shape.name, B) if args.ctx == "f32" else None,
         "traffic_source": ("committed ncu --set full capture %s (same shape and batch); not re-measured in this run"
                            % os.path.relpath(tf, ROOT)) if tf else None,
         "kernel": "fused lift-splat training step = plan + forward + backward kernels of one step (every kernel the "
-                  "library launches for %d frames)" % B,
+                  "library launches for %d frames), %s context" % (B, args.ctx),
         "algorithmic_bytes_per_launch": train_bytes, "launch_ms": train_ms, "windows": _stats(train_windows),
         "peak_source": peak_src, "frac_of_8TBs_nominal": train_achieved / 8000.0,
         "forward_only": {
             "kernel": "4x4 prep + plan + forward of one step, one CUDA-graph launch (the step `value` is computed from)",
             "algorithmic_bytes_per_launch": fwd_bytes, "launch_ms": step_ms, "achieved": fwd_achieved,
             "frac": fwd_achieved / peak, "windows": _stats(fwd_windows),
+            "traffic": _ncu_traffic(list(kern.keys()), shape.name, B),
             "kernel_sum_ms": lib_ms / K if K else 0.0},
         "dominant_kernel": dominant, "dominant_share": kern[dominant]["share"] if dominant else None,
         "kernels": kern,
@@ -543,6 +554,71 @@ def _time_loop(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+def shape_lines(args, dev, world, barrier):
+    """The other BASELINE.json configs, short, on EVERY rank (frames sharded like the headline): forward step (plan rebuilt
+    every step, CUDA-graph replay) and training step (plan + forward + backward) on the second mandatory shape SGV3D-BSM-R50,
+    the Rope3D-shaped ones (config 3) and the bf16-context training config (config 4: 8 frames per GPU).  Times are the max
+    over ranks; frames/s are whole-job aggregates."""
+    from sgv3d_b200 import LiftSplat, LiftSplatGraph
+    peak, _ = _peaks()
+    out = {}
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / iters
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    rank = _dist()[0]
+    for nm, nb, dt in (("sgv3d_bsm_r50", 16, torch.float32), ("rope3d_r50", 32, torch.float32),
+                       ("rope3d_native", 32, torch.float32), ("dair_r50", 8, torch.bfloat16),
+                       ("sgv3d_bsm_r50", 8, torch.bfloat16)):
+        sh = get_shape(nm)
+        m2 = LiftSplat(sh.x_bound, sh.y_bound, sh.z_bound, sh.d_bound, sh.final_dim, sh.downsample, sh.channels).to(dev)
+        mats2 = make_mats(sh, nb, 1, seed=77 + 1000 * rank, bda="identity")
+        md2 = _mats_dict(mats2, dev)
+        lg2, cx2 = make_activations(sh, nb, 1, seed=77 + 1000 * rank, device=dev, generator_device=dev)
+        key = f"{nm}_b{nb}_{'bf16ctx' if dt == torch.bfloat16 else 'f32'}"
+        rec = {"frames_per_gpu": nb, "n_gpus": world, "ctx_dtype": str(dt).split(".")[-1]}
+        ctx_b = 2 if dt == torch.bfloat16 else 4
+        fb2, bb2 = sh.fused_forward_bytes(ctx_b) * nb, sh.fused_backward_bytes(ctx_b) * nb
+        if dt == torch.float32:
+            hf2 = torch.cat((lg2, cx2), 1).contiguous()
+            g2 = LiftSplatGraph(m2, hf2, md2, warmup=1)
+            ms_f = timed(g2)
+            rec["forward_step"] = {"ms": ms_f, "frames_per_s": world * nb / (ms_f * 1e-3),
+                                   "frac_of_measured_peak": fb2 / ms_f / 1e6 / peak}
+            del g2
+        plan2 = m2.make_plan(md2, 0, sh.channels, dt)
+        cxd = cx2.to(dt)
+        gb2 = torch.randn(nb, sh.channels, sh.grid[1], sh.grid[0], device=dev)
+
+        def tstep():
+            plan2.rebuild()
+            plan2.forward(lg2, cxd, logits=True)
+            plan2.backward(gb2, lg2, cxd, logits=True)
+        ms_t = timed(tstep)
+        rec["train_step"] = {"ms": ms_t, "frames_per_s": world * nb / (ms_t * 1e-3), "algorithmic_bytes_per_gpu": fb2 + bb2,
+                             "achieved_GBs_per_gpu": (fb2 + bb2) / ms_t / 1e6,
+                             "frac_of_measured_peak": (fb2 + bb2) / ms_t / 1e6 / peak}
+        rec["pipeline"] = _pipeline_name(plan2)
+        out[key] = rec
+        del plan2, m2
+    return out
+
+
 def extra_measurements(args, shape, mod, sets, dev):
     """Secondary numbers (not the headline): training step, cached plan, batch-1 latency, the op-level
     drop-in."""
@@ -595,44 +671,6 @@ def extra_measurements(args, shape, mod, sets, dev):
         sweep[str(nb)] = nb / (_time_loop(gb_, 10) * 1e-3)
         del gb_, hfb, mdb
     out["frames_per_s_by_batch"] = sweep
-    # the other BASELINE.json configs, short: forward step (plan rebuilt every step, CUDA-graph replay) and training
-    # step (plan + forward + backward) on the second mandatory shape, the Rope3D-shaped ones and the bf16-context
-    # training config (config 4: batch 8 per GPU)
-    from sgv3d_b200 import LiftSplat
-    shapes_out = {}
-    for nm, nb, dt in (("sgv3d_bsm_r50", 16, torch.float32), ("rope3d_r50", 32, torch.float32),
-                       ("rope3d_native", 32, torch.float32), ("dair_r50", 8, torch.bfloat16),
-                       ("sgv3d_bsm_r50", 8, torch.bfloat16)):
-        sh = get_shape(nm)
-        m2 = LiftSplat(sh.x_bound, sh.y_bound, sh.z_bound, sh.d_bound, sh.final_dim, sh.downsample, sh.channels).to(dev)
-        mats2 = make_mats(sh, nb, 1, seed=77, bda="identity")
-        md2 = _mats_dict(mats2, dev)
-        lg2, cx2 = make_activations(sh, nb, 1, seed=77, device=dev, generator_device=dev)
-        key = f"{nm}_b{nb}_{'bf16ctx' if dt == torch.bfloat16 else 'f32'}"
-        rec = {"frames": nb, "ctx_dtype": str(dt).split(".")[-1]}
-        ctx_b = 2 if dt == torch.bfloat16 else 4
-        fb2, bb2 = sh.fused_forward_bytes(ctx_b) * nb, sh.fused_backward_bytes(ctx_b) * nb
-        if dt == torch.float32:
-            hf2 = torch.cat((lg2, cx2), 1).contiguous()
-            g2 = LiftSplatGraph(m2, hf2, md2, warmup=1)
-            ms_f = _time_loop(g2, 10)
-            rec["forward_step"] = {"ms": ms_f, "frames_per_s": nb / (ms_f * 1e-3), "frac_of_measured_peak": fb2 / ms_f / 1e6 / peak}
-            del g2
-        plan2 = m2.make_plan(md2, 0, sh.channels, dt)
-        cxd = cx2.to(dt)
-        gb2 = torch.randn(nb, sh.channels, sh.grid[1], sh.grid[0], device=dev)
-
-        def tstep():
-            plan2.rebuild()
-            plan2.forward(lg2, cxd, logits=True)
-            plan2.backward(gb2, lg2, cxd, logits=True)
-        ms_t = _time_loop(tstep, 10)
-        rec["train_step"] = {"ms": ms_t, "frames_per_s": nb / (ms_t * 1e-3), "algorithmic_bytes": fb2 + bb2,
-                             "achieved_GBs": (fb2 + bb2) / ms_t / 1e6, "frac_of_measured_peak": (fb2 + bb2) / ms_t / 1e6 / peak}
-        rec["pipeline"] = _pipeline_name(plan2)
-        shapes_out[key] = rec
-        del plan2, m2
-    out["shapes"] = shapes_out
     # op-level drop-in (materialised frustum features are an API input there); the reference's own kernel,
     # recompiled for sm_100a, is timed on the same inputs by tests/bench_reference_kernel.py (test infrastructure)
     nb = min(B, 4)
@@ -659,6 +697,7 @@ def main():
     ap.add_argument("--shape", default="dair_r50")
     ap.add_argument("--quick", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--repeats", type=int, default=5, help="timed windows of --steps steps each (median / p10 / p90)")
+    ap.add_argument("--ctx", default="f32", choices=["f32", "bf16"], help="context dtype of the training step (config 4: bf16)")
     ap.add_argument("--eager", action="store_true", help="time per-kernel launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -204,6 +204,19 @@ SGV3D_API int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, const
                               float *grad_context, void *workspace, size_t workspace_bytes,
                               sgv3d_stream_t stream);
 
+/* Backward of the BSMLSSFPN call site with the context assembly fused (bsm_lss_fpn.py:523-541 under autograd): the
+ * kernel re-assembles cat(context, softmax(semantic_logits)) * (1 - background mask) per pixel chunk in shared
+ * memory, so neither pass ever materialises the C-channel tensor, and pixels masked as background are skipped (all
+ * their gradients are exact zeros).  grad_context fp32 [B*Nc, C - Cs, fH, fW], grad_semantic fp32 [B*Nc, Cs, fH, fW]
+ * (gradient w.r.t. the semantic LOGITS: softmax backward; the mask itself is not differentiable), grad_height as in
+ * sgv3d_lift_splat_backward.  Cs <= 8, C <= 96, fp32 context, voxel-tile pipeline. */
+SGV3D_API int sgv3d_lift_splat_backward_bsm(const sgv3d_lift_splat_desc *desc, const float *grad_bev,
+                                  const float *height, const float *context, const float *semantic_logits,
+                                  int semantic_channels, int64_t semantic_batch_stride,
+                                  float background_threshold, float *grad_height, float *grad_context,
+                                  float *grad_semantic, void *workspace, size_t workspace_bytes,
+                                  sgv3d_stream_t stream);
+
 /* Debug / parity: expand the plan back to one voxel id per point.
  * vox_out int32 [B, Nc, D, fH, fW]: y*X + x of the voxel the point falls in, -1 if dropped. */
 SGV3D_API int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, int32_t *vox_out,

@@ -24,7 +24,7 @@ SYMBOLS = (
     "sgv3d_geometry_quantize", "sgv3d_inverse4x4", "sgv3d_camera_prep",
     "sgv3d_lift_splat_workspace_bytes", "sgv3d_lift_splat_plan", "sgv3d_lift_splat_forward",
     "sgv3d_lift_splat_forward_bsm", "sgv3d_lift_splat_backward", "sgv3d_lift_splat_plan_expand",
-    "sgv3d_lift_splat_uses_block_pipeline",
+    "sgv3d_lift_splat_uses_block_pipeline", "sgv3d_lift_splat_backward_bsm",
     "sgv3d_profile_enable", "sgv3d_profile_report",
 )
 
@@ -86,6 +86,9 @@ def lib() -> ctypes.CDLL:
                                                + [c_void_p] * 2 + [c_size_t, c_void_p])
     L.sgv3d_lift_splat_backward.restype = c_int
     L.sgv3d_lift_splat_backward.argtypes = [P] + [c_void_p] * 6 + [c_size_t, c_void_p]
+    L.sgv3d_lift_splat_backward_bsm.restype = c_int
+    L.sgv3d_lift_splat_backward_bsm.argtypes = ([P] + [c_void_p] * 4 + [c_int, c_int64, ctypes.c_float]
+                                                + [c_void_p] * 4 + [c_size_t, c_void_p])
     L.sgv3d_lift_splat_plan_expand.restype = c_int
     L.sgv3d_lift_splat_plan_expand.argtypes = [P] + [c_void_p] * 2 + [c_size_t, c_void_p]
     L.sgv3d_profile_enable.restype = c_int

@@ -1326,18 +1326,21 @@ ls_grad_rows_kernel(Dims m, const float *__restrict__ grad_bev, const int *__res
 constexpr int kBwdPix = 64;    // pixels per CTA (half a plan chunk)
 constexpr int kBwdLd = kBwdPix + 1;
 
-template <typename CT, int NV, int OCC>
+template <typename CT, int NV, int OCC, bool BSM>
 __global__ void __launch_bounds__(kBwdPix * 4, OCC)
 ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, int vec16_out,
-                         const CT *__restrict__ context, const float *__restrict__ gT, const int *__restrict__ run_cnt,
+                         const CT *__restrict__ context, BsmAssembly bsm, float *__restrict__ g_semantic,
+                         const float *__restrict__ gT, const int *__restrict__ run_cnt,
                          const int *__restrict__ run_vox, const int *__restrict__ run_d,
                          float *__restrict__ w_pm, float *__restrict__ gw_pm, float *__restrict__ g_height,
                          float *__restrict__ g_context) {
   constexpr int G = 4, NJ = 4 * NV;   // NJ channels per lane
   constexpr int kRowF = 4 * G * NV;   // floats per gradient row (= Cpad)
-  extern __shared__ float bsm[];
-  float *col = bsm;                          // [D][64]   height bins, then exp(x - max)
-  float *tile = bsm + m.D * kBwdPix;         // [Cpad][65] context in, g_ctx out
+  extern __shared__ float bwd_smem[];
+  __shared__ float s_keep[BSM ? kBwdPix : 1];        // BSM: 0 for background pixels
+  __shared__ float s_semp[BSM ? 8 : 1][kBwdPix];     // BSM: semantic probabilities (Cs <= 8)
+  float *col = bwd_smem;                     // [D][64]   height bins, then exp(x - max)
+  float *tile = bwd_smem + m.D * kBwdPix;    // [Cpad][65] context in, g_ctx out
   const int b = blockIdx.y;
   const int chunk = blockIdx.x >> 1, half = blockIdx.x & 1;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
@@ -1360,23 +1363,53 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
       const float *hs = height + (size_t)bn * m.hs + p0 + t;
       for (int d = q; d < m.D; d += 4) cp_async_4(col + d * kBwdPix + t, hs + (size_t)d * m.P);
     }
+    const int Cc = m.C - (BSM ? bsm.Cs : 0);   // channels that come from `context`
     if (t < npx) {
       const CT *cs = context + (size_t)bn * m.cs + p0 + t;
       if (sizeof(CT) == 4) {
-        for (int c = q; c < m.C; c += 4)
+        for (int c = q; c < Cc; c += 4)
           cp_async_4(tile + c * kBwdLd + t, reinterpret_cast<const float *>(cs) + (size_t)c * m.P);
+        if (BSM) {
+          const float *ss = bsm.sem + (size_t)bn * bsm.sem_stride + p0 + t;
+          for (int k = q; k < bsm.Cs; k += 4) cp_async_4(tile + (Cc + k) * kBwdLd + t, ss + (size_t)k * m.P);
+        }
       } else {
-        for (int c = q; c < m.C; c += 4) tile[c * kBwdLd + t] = to_f32<CT>(cs[(size_t)c * m.P]);
+        for (int c = q; c < Cc; c += 4) tile[c * kBwdLd + t] = to_f32<CT>(cs[(size_t)c * m.P]);
       }
     }
     cp_async_wait_all();
     __syncthreads();
+    if (BSM) {  // block-uniform
+      // BSMLSSFPN context assembly (bsm_lss_fpn.py:524-529), as in the forward's context pass: semantic =
+      // softmax(logits) in torch's channel-softmax order, rows = cat(context, semantic) * (1 - (semantic[0] > thr)).
+      // The unmasked probabilities stay in s_semp for the softmax backward at the end.
+      if (tid < kBwdPix) {
+        float keep = 1.0f;
+        if (tid < npx) {
+          float *colp = tile + Cc * kBwdLd + tid;
+          float mx = colp[0];
+          for (int k = 1; k < bsm.Cs; ++k) mx = fmaxf(mx, colp[k * kBwdLd]);
+          float sum = 0.0f;
+          for (int k = 0; k < bsm.Cs; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(colp[k * kBwdLd], mx)));
+          for (int k = 0; k < bsm.Cs; ++k) {
+            const float pk = __fdiv_rn(expf(__fsub_rn(colp[k * kBwdLd], mx)), sum);
+            s_semp[k][tid] = pk;
+            colp[k * kBwdLd] = pk;
+          }
+          keep = colp[0] > bsm.thr ? 0.0f : 1.0f;
+        }
+        s_keep[tid] = keep;
+      }
+      __syncthreads();
+      // (masked pixels are skipped below: every gradient of theirs is an exact zero)
+    }
   }
 
   const int px = tid >> 2, l = tid & 3;       // group = pixel, lane inside the group
   const bool live = px < npx;
   const int tch = half * kBwdPix + px;        // thread index of this pixel inside the plan chunk
-  const int cnt = live ? run_cnt[(size_t)frame_chunk * kChunk + tch] : 0;
+  const bool masked = BSM && s_keep[px] == 0.0f;
+  const int cnt = (live && !masked) ? run_cnt[(size_t)frame_chunk * kChunk + tch] : 0;
 
   // ---- 2. softmax over D -----------------------------------------------------------------------------
   float scale = 1.0f;
@@ -1521,9 +1554,19 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
   // ---- 4b. g_ctx tile -> NCHW rows (256-byte segments) ------------------------------------------------
   {
     const int t = tid & (kBwdPix - 1), q = tid >> 6;
+    const int Cc = m.C - (BSM ? bsm.Cs : 0);
     if (t < npx) {
       float *gc = g_context + (size_t)bn * m.gcs + p0 + t;
-      for (int c = q; c < m.C; c += 4) stg_stream_f1(gc + (size_t)c * m.P, tile[c * kBwdLd + t]);
+      for (int c = q; c < Cc; c += 4) stg_stream_f1(gc + (size_t)c * m.P, tile[c * kBwdLd + t]);
+      if (BSM && q == 0) {
+        // backward of semantic = softmax(logits) (the mask is not differentiable; masked pixels hold zeros):
+        // g_logit_k = p_k (g_k - sum_j p_j g_j), channel order
+        float dot = 0.0f;
+        for (int k = 0; k < bsm.Cs; ++k) dot = __fmaf_rn(s_semp[k][t], tile[(Cc + k) * kBwdLd + t], dot);
+        float *gs = g_semantic + (size_t)bn * bsm.Cs * m.P + p0 + t;
+        for (int k = 0; k < bsm.Cs; ++k)
+          stg_stream_f1(gs + (size_t)k * m.P, __fmul_rn(s_semp[k][t], __fsub_rn(tile[(Cc + k) * kBwdLd + t], dot)));
+      }
     }
   }
 }
@@ -1642,7 +1685,8 @@ int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s)
 
 template <typename CT, int NV>
 int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *height, const void *context,
-                              float *grad_height, float *grad_context, cudaStream_t s) {
+                              float *grad_height, float *grad_context, cudaStream_t s, BsmAssembly bsm,
+                              float *grad_semantic) {
   const size_t smem = sizeof(float) * ((size_t)m.D * kBwdPix + (size_t)m.Cpad * kBwdLd);
   // CTAs per SM: the kernel is latency bound (dependent gather -> FMA -> shuffle chains), so a third resident CTA pays
   // for the ~14 words of spill it costs at <= 80 channels (DAIR-R50: 440 -> 385 us at 64 frames); with 96-float rows
@@ -1653,10 +1697,17 @@ int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *he
   const int occ = occ_env ? occ_env : (NV <= 3 ? 4 : (NV <= 5 ? 3 : 2));
 #define SGV3D_BWD_CHUNK(OCC)                                                                                   \
   do {                                                                                                         \
-    if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC>, smem)) return rc;                             \
-    ls_backward_chunk_kernel<CT, NV, OCC><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(                 \
-        m, height, vec16, vec16_out, static_cast<const CT *>(context), w.gT, w.run_cnt, w.run_vox, w.run_d,    \
-        w.w_pm, w.gw_pm, grad_height, grad_context);                                                           \
+    if (bsm.sem) {                                                                                             \
+      if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, true>, smem)) return rc;                     \
+      ls_backward_chunk_kernel<CT, NV, OCC, true><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(         \
+          m, height, vec16, vec16_out, static_cast<const CT *>(context), bsm, grad_semantic, w.gT, w.run_cnt,  \
+          w.run_vox, w.run_d, w.w_pm, w.gw_pm, grad_height, grad_context);                                     \
+      break;                                                                                                   \
+    }                                                                                                          \
+    if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, false>, smem)) return rc;                      \
+    ls_backward_chunk_kernel<CT, NV, OCC, false><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(          \
+        m, height, vec16, vec16_out, static_cast<const CT *>(context), bsm, grad_semantic, w.gT, w.run_cnt,    \
+        w.run_vox, w.run_d, w.w_pm, w.gw_pm, grad_height, grad_context);                                       \
   } while (0)
   if (occ >= 4) SGV3D_BWD_CHUNK(4);
   else if (occ == 3) SGV3D_BWD_CHUNK(3);
@@ -1668,14 +1719,15 @@ int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *he
 
 template <typename CT>
 int launch_backward_chunk(const Dims &m, const Workspace &w, const float *height, const void *context,
-                          float *grad_height, float *grad_context, cudaStream_t s) {
+                          float *grad_height, float *grad_context, cudaStream_t s,
+                          BsmAssembly bsm = BsmAssembly{nullptr, 0, 0, 0.0f}, float *grad_semantic = nullptr) {
   switch (m.NV) {
-    case 1: return launch_backward_chunk_cfg<CT, 1>(m, w, height, context, grad_height, grad_context, s);
-    case 2: return launch_backward_chunk_cfg<CT, 2>(m, w, height, context, grad_height, grad_context, s);
-    case 3: return launch_backward_chunk_cfg<CT, 3>(m, w, height, context, grad_height, grad_context, s);
-    case 4: return launch_backward_chunk_cfg<CT, 4>(m, w, height, context, grad_height, grad_context, s);
-    case 5: return launch_backward_chunk_cfg<CT, 5>(m, w, height, context, grad_height, grad_context, s);
-    default: return launch_backward_chunk_cfg<CT, 6>(m, w, height, context, grad_height, grad_context, s);
+    case 1: return launch_backward_chunk_cfg<CT, 1>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
+    case 2: return launch_backward_chunk_cfg<CT, 2>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
+    case 3: return launch_backward_chunk_cfg<CT, 3>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
+    case 4: return launch_backward_chunk_cfg<CT, 4>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
+    case 5: return launch_backward_chunk_cfg<CT, 5>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
+    default: return launch_backward_chunk_cfg<CT, 6>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
   }
 }
 
@@ -1718,7 +1770,8 @@ int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const flo
 
 int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, const float *grad_bev,
                           const float *height, const void *context, float *grad_height, float *grad_context,
-                          cudaStream_t s) {
+                          cudaStream_t s, BsmAssembly bsm = BsmAssembly{nullptr, 0, 0, 0.0f},
+                          float *grad_semantic = nullptr) {
   // grad_bev -> one row per voxel, then everything else per pixel chunk in one kernel
   const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
   if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
@@ -1726,7 +1779,7 @@ int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, cons
   SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
   return ctx_dtype == SGV3D_DTYPE_BF16
              ? launch_backward_chunk<__nv_bfloat16>(m, w, height, context, grad_height, grad_context, s)
-             : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s);
+             : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
 }
 
 // Which pipeline serves this descriptor: desc->reserved[0] = 0 (auto), 1 (voxel-tile pipeline of this file),
@@ -1933,6 +1986,42 @@ extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, cons
                                         (size_t)m.P * gpad, m.P, (size_t)m.gcs, s, row_perm(m));
   SGV3D_CHECK_LAUNCH("transpose_pad_kernel(grad_context)");
   return SGV3D_OK;
+}
+
+extern "C" int sgv3d_lift_splat_backward_bsm(const sgv3d_lift_splat_desc *desc, const float *grad_bev,
+                                             const float *height, const float *context,
+                                             const float *semantic_logits, int semantic_channels,
+                                             int64_t semantic_batch_stride, float background_threshold,
+                                             float *grad_height, float *grad_context, float *grad_semantic,
+                                             void *workspace, size_t workspace_bytes, sgv3d_stream_t stream) {
+  if (int rc = validate(desc, "lift_splat_backward_bsm")) return rc;
+  if (desc->B == 0) return SGV3D_OK;
+  SGV3D_REQUIRE(grad_bev && height && context && semantic_logits && grad_height && grad_context && grad_semantic,
+                "lift_splat_backward_bsm: null pointer");
+  SGV3D_REQUIRE(desc->ctx_dtype == SGV3D_DTYPE_F32, "lift_splat_backward_bsm: fp32 context only");
+  SGV3D_REQUIRE(semantic_channels > 0 && semantic_channels <= 8 && semantic_channels < desc->C,
+                "lift_splat_backward_bsm: semantic_channels must be in [1, 8] and < C");
+  SGV3D_REQUIRE(desc->C <= 96, "lift_splat_backward_bsm: C <= 96 (fused backward)");
+  SGV3D_REQUIRE(semantic_batch_stride >= 0, "lift_splat_backward_bsm: negative batch stride");
+  Dims m = make_dims(desc);
+  SGV3D_REQUIRE(!use_block(desc, m), "lift_splat_backward_bsm: voxel-tile pipeline only");
+  const int Cc = m.C - semantic_channels;
+  // `context` / `grad_context` hold the C - Cs feature channels: their dense camera blocks are that much smaller
+  if (!desc->ctx_batch_stride) m.cs = (long long)Cc * m.P;
+  if (!desc->grad_ctx_batch_stride) m.gcs = (long long)Cc * m.P;
+  const Workspace w = carve(workspace, m, desc->ctx_dtype);
+  if (int rc = check_ws(w, workspace, workspace_bytes, "lift_splat_backward_bsm")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  prof_begin(s);
+  BsmAssembly bsm;
+  bsm.sem = semantic_logits;
+  bsm.sem_stride = semantic_batch_stride ? semantic_batch_stride : (long long)semantic_channels * m.P;
+  bsm.Cs = semantic_channels;
+  bsm.thr = background_threshold;
+  Dims mb = m;
+  mb.G = 4; mb.NV = ceil_div(m.C, 16); mb.Cpad = 16 * mb.NV;
+  return launch_backward_fused(mb, w, desc->ctx_dtype, grad_bev, height, context, grad_height, grad_context, s, bsm,
+                               grad_semantic);
 }
 
 extern "C" int sgv3d_lift_splat_plan_expand(const sgv3d_lift_splat_desc *desc, int32_t *vox_out,

@@ -372,6 +372,38 @@ class LiftSplatPlan:
                                                          self.ws_bytes, N.current_stream()))
         return bev
 
+    def uses_block_pipeline(self) -> bool:
+        return bool(N.lib().sgv3d_lift_splat_uses_block_pipeline(self.desc))
+
+    def backward_bsm(self, grad_bev: torch.Tensor, height: torch.Tensor, context: torch.Tensor,
+                     semantic_logits: torch.Tensor, threshold: float = 0.45, logits: bool = True):
+        """Gradients of the BSMLSSFPN call site with the context assembly fused (bsm_lss_fpn.py:523-541 under autograd):
+        (grad_height [logits], grad_context (BN, C - Cs, fH, fW), grad_semantic_logits (BN, Cs, fH, fW))."""
+        d = self.desc
+        bn, cs = d.B * d.Nc, int(semantic_logits.shape[1])
+        cc = d.C - cs
+        g = grad_bev.float().contiguous()
+        assert tuple(g.shape) == (d.B, d.C, d.Y, d.X)
+        height, context, semantic_logits = _dense_blocks(height), _dense_blocks(context), _dense_blocks(semantic_logits)
+        for name, t, ch in (("height", height, d.D), ("context", context, cc), ("semantic_logits", semantic_logits, cs)):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise RuntimeError(f"backward_bsm: {name} must be a float32 CUDA tensor")
+            assert tuple(t.shape) == (bn, ch, d.fH, d.fW), (name, tuple(t.shape), (bn, ch, d.fH, d.fW))
+        g_height = torch.empty(bn, d.D, d.fH, d.fW, dtype=torch.float32, device=self.device)
+        g_ctx = torch.empty(bn, cc, d.fH, d.fW, dtype=torch.float32, device=self.device)
+        g_sem = torch.empty(bn, cs, d.fH, d.fW, dtype=torch.float32, device=self.device)
+        c = N.LiftSplatDesc.from_buffer_copy(d)
+        c.height_is_logits = 1 if logits else 0
+        c.height_batch_stride = _camera_block_stride(height, d.D, d.fH, d.fW, "height")
+        c.ctx_batch_stride = _camera_block_stride(context, cc, d.fH, d.fW, "context")
+        sem_stride = _camera_block_stride(semantic_logits, cs, d.fH, d.fW, "semantic_logits")
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sgv3d_lift_splat_backward_bsm(c, N.ptr(g), N.ptr(height), N.ptr(context),
+                                                          N.ptr(semantic_logits), cs, sem_stride, float(threshold),
+                                                          N.ptr(g_height), N.ptr(g_ctx), N.ptr(g_sem), N.ptr(self.ws),
+                                                          self.ws_bytes, N.current_stream()))
+        return g_height, g_ctx, g_sem
+
     def backward(self, grad_bev: torch.Tensor, height: torch.Tensor, context: torch.Tensor, logits: bool = False,
                  out_height: Optional[torch.Tensor] = None, out_context: Optional[torch.Tensor] = None):
         """Gradients w.r.t. ``height`` (w.r.t. the logits when ``logits=True``) and ``context``; optionally
@@ -455,6 +487,25 @@ class _LiftSplatHeadFunction(Function):
         ctx.plan.backward(grad_bev, hf[:, :d], hf[:, d:d + c], logits=True,
                           out_height=g[:, :d], out_context=g[:, d:d + c])
         return g, None, None, None
+
+
+class _LiftSplatBsmFunction(Function):
+    """BSMLSSFPN call site under autograd with the context assembly (7-way semantic softmax, concat, background mask:
+    bsm_lss_fpn.py:524-529) fused into both passes: the 87-channel masked tensor is never built, masked pixels are
+    skipped, and the semantic-softmax backward runs inside the backward kernel."""
+
+    @staticmethod
+    def forward(ctx, height_logits, semantic_logits, context, plan: LiftSplatPlan, threshold: float):
+        h, s, c = _dense_blocks(height_logits), _dense_blocks(semantic_logits), _dense_blocks(context)
+        ctx.plan, ctx.threshold = plan, threshold
+        ctx.save_for_backward(h, s, c)
+        return plan.forward_bsm(h, c, s, threshold, logits=True)
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        h, s, c = ctx.saved_tensors
+        g_h, g_c, g_s = ctx.plan.backward_bsm(grad_bev, h, c, s, ctx.threshold, logits=True)
+        return g_h, g_s, g_c, None, None
 
 
 def lift_splat(height: torch.Tensor, context: torch.Tensor, plan: LiftSplatPlan, logits: bool = False) -> torch.Tensor:
@@ -581,14 +632,22 @@ class LiftSplat(nn.Module):
     def forward_single_sweep_bsm(self, height_logits, semantic_logits, context, mats_dict,
                                  sweep_index: int = 0) -> torch.Tensor:
         """BSMLSSFPN: ``out[0], out[1], out[2]`` of the MSCT head (bsm_lss_fpn.py:522-529): height
-        logits (BN, D, fH, fW), 7 semantic logits, 80 context channels.  The 87-channel masked context
-        is assembled exactly as the reference does, then lifted and splatted."""
+        logits (BN, D, fH, fW), 7 semantic logits, 80 context channels.  The 87-channel masked context of the
+        reference (softmax, concat, background mask) is assembled inside the kernels, in the forward and -- under
+        autograd -- in the backward as well (the torch assembly remains for the pixel-block pipeline, > 8 semantic
+        channels, > 96 channels or non-fp32 context)."""
         if not (torch.is_grad_enabled() and (height_logits.requires_grad or semantic_logits.requires_grad
                                              or context.requires_grad)):
             # inference: softmax over the 7 semantic channels, concat and background mask (bsm_lss_fpn.py:524-529)
             # run inside the forward's context pass; the 87-channel tensor is never built
             plan = self.make_plan(mats_dict, sweep_index, int(context.shape[1] + semantic_logits.shape[1]))
             return plan.forward_bsm(height_logits.float(), context.float(), semantic_logits.float(), 0.45)
+        c_all = int(context.shape[1] + semantic_logits.shape[1])
+        if c_all <= 96 and semantic_logits.shape[1] <= 8 and context.dtype == torch.float32:
+            plan = self.make_plan(mats_dict, sweep_index, c_all)
+            if not plan.uses_block_pipeline():
+                # training: assembly and its backward fused into the kernels (no 87-channel tensor in either pass)
+                return _LiftSplatBsmFunction.apply(height_logits.float(), semantic_logits.float(), context, plan, 0.45)
         semantic = semantic_logits.softmax(dim=1)                               # bsm_lss_fpn.py:524
         tran_feat = torch.cat((context, semantic), dim=1)                       # :526
         mask = semantic[:, 0, :, :].unsqueeze(1) > 0.45                         # :528 background
