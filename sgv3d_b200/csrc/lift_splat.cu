@@ -639,10 +639,13 @@ __device__ __forceinline__ void stage_columns(float *col, const float *__restric
   const int tid = threadIdx.x;
   const int npx = min(kChunk, P - p0);
   if (vec16 && npx == kChunk) {
-    // one warp copies one 512-byte row per instruction
-    const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    for (int d = wid; d < D; d += nw)
-      cp_async_16(col + d * kChunk + lane * 4, src + (size_t)d * P + p0 + lane * 4);
+    // bulk-async copies (TMA engine): one instruction per 512-byte row, completion on an mbarrier
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    bulk_stage_rows(col, kChunk * sizeof(float), src + p0, (size_t)P * sizeof(float), D, kChunk * sizeof(float), &s_bar);
+    mbar_wait(&s_bar, 0);
+    return;
   } else {
     const int t = tid & (kChunk - 1), q = tid / kChunk, nq = blockDim.x / kChunk;
     if (t < npx)
@@ -884,7 +887,7 @@ ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const i
                     const int *__restrict__ run_d, const int *__restrict__ run_dst,
                     float *__restrict__ w_pm_out, Entry *__restrict__ vm_ent_out,
                     const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm, BsmAssembly bsm) {
-  extern __shared__ float lift_smem[];
+  extern __shared__ __align__(128) float lift_smem[];
   if (blockIdx.z == 0)
     weights_role(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x);
   else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x, bsm);
@@ -1336,7 +1339,8 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
                          float *__restrict__ g_context) {
   constexpr int G = 4, NJ = 4 * NV;   // NJ channels per lane
   constexpr int kRowF = 4 * G * NV;   // floats per gradient row (= Cpad)
-  extern __shared__ float bwd_smem[];
+  extern __shared__ __align__(128) float bwd_smem[];
+  __shared__ __align__(8) unsigned long long s_bar;  // completion of the bulk-async height block
   __shared__ float s_keep[BSM ? kBwdPix : 1];        // BSM: 0 for background pixels
   __shared__ float s_semp[BSM ? 8 : 1][kBwdPix];     // BSM: semantic probabilities (Cs <= 8)
   float *col = bwd_smem;                     // [D][64]   height bins, then exp(x - max)
@@ -1354,11 +1358,13 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
   // ---- 1. stage ------------------------------------------------------------------------------------
   {
     const int t = tid & (kBwdPix - 1), q = tid >> 6;  // 4 quarter-blocks of threads, each walks a share of the rows
-    if (vec16 && npx == kBwdPix) {
-      // 16 lanes copy one 256-byte row of the height block per instruction
-      const int t4 = tid & 15;
-      const float *hs = height + (size_t)bn * m.hs + p0 + 4 * t4;
-      for (int d = tid >> 4; d < m.D; d += (kBwdPix * 4) >> 4) cp_async_16(col + d * kBwdPix + 4 * t4, hs + (size_t)d * m.P);
+    const bool bulk = vec16 && npx == kBwdPix;   // block-uniform
+    if (bulk) {
+      // bulk-async copies (TMA engine): one instruction per 256-byte row of the height block
+      if (tid == 0) mbar_init(&s_bar, 1);
+      __syncthreads();
+      bulk_stage_rows(col, kBwdPix * sizeof(float), height + (size_t)bn * m.hs + p0, (size_t)m.P * sizeof(float), m.D,
+                      kBwdPix * sizeof(float), &s_bar);
     } else if (t < npx) {
       const float *hs = height + (size_t)bn * m.hs + p0 + t;
       for (int d = q; d < m.D; d += 4) cp_async_4(col + d * kBwdPix + t, hs + (size_t)d * m.P);
@@ -1378,6 +1384,7 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
       }
     }
     cp_async_wait_all();
+    if (bulk) mbar_wait(&s_bar, 0);
     __syncthreads();
     if (BSM) {  // block-uniform
       // BSMLSSFPN context assembly (bsm_lss_fpn.py:524-529), as in the forward's context pass: semantic =
@@ -1583,7 +1590,7 @@ ls_expand_kernel(Dims m, const float *__restrict__ height, int vec16, const int 
                  const int *__restrict__ run_d, const int *__restrict__ run_vox,
                  const float *__restrict__ w_pm, const float *__restrict__ gw_pm,
                  float *__restrict__ g_height, int *__restrict__ vox_out) {
-  extern __shared__ float col[];
+  extern __shared__ __align__(128) float col[];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;

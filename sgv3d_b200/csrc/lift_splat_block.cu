@@ -691,6 +691,7 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
   constexpr int kCpad = 32 * NV;
   constexpr int kLd = kBP + 1;
   extern __shared__ __align__(16) float bsm_[];
+  __shared__ __align__(8) unsigned long long s_bar;
   const int b = blockIdx.y, kb = blockIdx.x;
   const size_t fbk = (size_t)b * m.NB + kb;
   const BlockInfo bi = info[fbk];
@@ -710,11 +711,14 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
 
   // ---- stage (all asynchronous) ------------------------------------------------------------------------
   stage_block_columns(col, height + (size_t)bn * m.hs, m, o, vec16 != 0);
-  {
-    const int nst = min(bi.max_runs, kRunsStaged);
-    const int *rsrc = rd_in + fbk * m.D * kBP;
-    for (int i = tid; i < nst * (kBP / 4); i += kFwdThreads)
-      cp_async_16(reinterpret_cast<float *>(rd_s) + 4 * i, reinterpret_cast<const float *>(rsrc) + 4 * i);
+  const int nst = min(bi.max_runs, kRunsStaged);
+  if (nst > 0) {
+    // run descriptors of the first kRunsStaged runs: one contiguous block, one bulk-async copy (TMA engine)
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_arrive_expect_tx(&s_bar, (unsigned)nst * kBP * 4);
+      bulk_copy_g2s(rd_s, rd_in + fbk * m.D * kBP, (unsigned)nst * kBP * 4, &s_bar);
+    }
   }
   cp_async_commit();
   {
@@ -734,11 +738,12 @@ bp_backward_kernel(BDims m, int cap, const float *__restrict__ height, int vec16
   float *gwp = gw_ws + fbk * m.D * kBP + t;
   const uint2 *ft = ftab + fbk * m.nstrips;
   const float *gb = grad_bev + (size_t)b * m.C * m.V;
-  cp_async_wait_group<1>();   // columns + run descriptors
-  __syncthreads();
+  cp_async_wait_group<1>();   // columns
+  __syncthreads();            // (also: the mbarrier initialised by thread 0 is visible to every waiter below)
   float scale = 1.0f;
   if (m.logits) scale = softmax_block_column(col, m.D, t, l, gmask);
   cp_async_wait_group<0>();   // context
+  if (nst > 0) mbar_wait(&s_bar, 0);   // run descriptors
   __syncthreads();
   float cx[NV][4], acc[NV][4];
 #pragma unroll

@@ -76,6 +76,46 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
 }
 
 
+// ---- bulk-async (TMA engine) row copies: cp.async.bulk global -> shared, completion on an mbarrier ----------------
+// One instruction moves a whole contiguous row (a multiple of 16 bytes, 16-byte aligned on both sides) without
+// touching registers or the LSU; the issuing thread only names source, destination, size and the barrier.  Usage:
+//   thread 0: mbar_init(bar, 1); fence; __syncthreads();
+//   thread 0: mbar_arrive_expect_tx(bar, total_bytes);   any thread(s): bulk_copy_g2s(dst, src, bytes, bar) ...
+//   every consumer: mbar_wait(bar, phase) -- returns once all `total_bytes` have landed (acquire: the data is visible).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MBAR_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra MBAR_WAIT_%=;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// rows of `row_bytes` (multiple of 16, both sides 16-byte aligned): row r from gsrc + r * src_stride_bytes to
+// smem_dst + r * dst_stride_bytes.  Called by all threads of the CTA after the barrier was initialised; returns without
+// waiting (mbar_wait(bar, phase) does).
+__device__ __forceinline__ void bulk_stage_rows(void *smem_dst, unsigned dst_stride_bytes, const void *gsrc,
+                                                size_t src_stride_bytes, int nrows, unsigned row_bytes,
+                                                unsigned long long *bar) {
+  if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (unsigned)nrows * row_bytes);
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x)
+    bulk_copy_g2s(static_cast<char *>(smem_dst) + (size_t)r * dst_stride_bytes,
+                  static_cast<const char *>(gsrc) + (size_t)r * src_stride_bytes, row_bytes, bar);
+}
+
 // exp(x) through the hardware 2^t unit (MUFU.EX2) with a compensated argument: t = x * log2(e) is formed as
 // t_hi + t_lo (t_hi the rounded leading product, t_lo its exact residual plus the low part of log2(e)), and
 // 2^(t_hi + t_lo) = 2^t_hi * (1 + t_lo ln 2) to first order (|t_lo| < 2^-20 for |x| < 100).  Error ~2 ulp
