@@ -31,53 +31,74 @@ constexpr int kScanThreads = 1024;
 static __global__ void __launch_bounds__(kScanThreads)
 scan_hist_kernel(int *__restrict__ hist, int bins, int nblk_max, const int *__restrict__ n_items,
                  int items_per_block, int *__restrict__ total_out) {
+  // One CTA per frame, row-wise: a bin's per-block counts are contiguous (hist[bin][blk]), so a warp reads a whole
+  // row with coalesced loads.  1. row totals (warp w owns the rows w, w + 32, ...), 2. exclusive scan of the bin
+  // totals (bins <= 1024: one value per thread), 3. every row rewritten with its exclusive prefixes, 32 blocks per
+  // step through a warp scan.  (Walking the bin-major sequence with one CTA cost 57 dependent steps, walking it with
+  // a contiguous range per thread 175 k uncoalesced sector requests from one SM: ~55 us per frame either way.)
+  __shared__ int row_tot[kMaxHighBins];
   __shared__ int warp_tot[kScanThreads / kWarp];
-  __shared__ int carry_s;
   const int frame = blockIdx.x;
   int nblk = nblk_max;
   if (n_items) nblk = (n_items[frame] + items_per_block - 1) / items_per_block;
   int *h = hist + (size_t)frame * bins * nblk_max;
-  const int L = bins * nblk;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (t == 0) carry_s = 0;
+  constexpr int kWarps_ = kScanThreads / kWarp;
+  for (int row = wid; row < bins; row += kWarps_) {
+    const int *r = h + (size_t)row * nblk_max;
+    int sum = 0;
+    int j = lane;
+    for (; j + 96 < nblk; j += 128) sum += (r[j] + r[j + 32]) + (r[j + 64] + r[j + 96]);
+    for (; j < nblk; j += 32) sum += r[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) row_tot[row] = sum;
+  }
   __syncthreads();
-  for (int base = 0; base < L; base += kScanThreads) {
-    const int k = base + t;
-    int v = 0;
-    size_t addr = 0;
-    if (k < L) {
-      const int bin = k / nblk, blk = k - bin * nblk;
-      addr = (size_t)bin * nblk_max + blk;
-      v = h[addr];
-    }
-    // inclusive warp scan
-    int x = v;
+  // exclusive scan of the bin totals
+  const int mine = t < bins ? row_tot[t] : 0;
+  int x = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    const int w = warp_tot[lane];
+    int xs = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      const int y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
     }
-    if (lane == 31) warp_tot[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      int w = warp_tot[lane];
-      int xs = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, xs, o);
-        if (lane >= o) xs += y;
-      }
-      warp_tot[lane] = xs - w;  // exclusive prefix of warp totals
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    const int excl = carry + warp_tot[wid] + x - v;
-    if (k < L) h[addr] = excl;
-    __syncthreads();
-    if (t == kScanThreads - 1) carry_s = excl + v;  // running total after this tile
-    __syncthreads();
+    warp_tot[lane] = xs - w;
+    if (lane == 31 && total_out) total_out[frame] = xs;
   }
-  if (t == 0 && total_out) total_out[frame] = carry_s;
+  __syncthreads();
+  if (t < bins) row_tot[t] = warp_tot[wid] + x - mine;   // first position of the bin
+  __syncthreads();
+  for (int row = wid; row < bins; row += kWarps_) {
+    int *r = h + (size_t)row * nblk_max;
+    int carry = row_tot[row];
+    for (int j0 = 0; j0 < nblk; j0 += 128) {   // four 32-block steps per round trip
+      int v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (j0 + 32 * u + lane < nblk) ? r[j0 + 32 * u + lane] : 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int xx = v[u];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, xx, o);
+          if (lane >= o) xx += y;
+        }
+        if (j0 + 32 * u + lane < nblk) r[j0 + 32 * u + lane] = carry + xx - v[u];
+        carry += __shfl_sync(0xffffffffu, xx, 31);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -102,11 +102,13 @@ vp_reduce_kernel(int N, int C, int V, const float *__restrict__ feat,
     const int cnt = min(32, hi - j0);
     const int mine = (lane < cnt) ? perm[j0 + lane] : 0;
     int i = 0;
-    // 4 rows in flight per warp before the dependent adds
-    for (; i + 4 <= cnt; i += 4) {
-      float r[4][NCH][VEC];
+    // kInFlight rows in flight per warp before the dependent adds: a warp owns one voxel, the most populated voxels
+    // (855 points at DAIR-R50) set the kernel's tail at small batches, and their time is rows / kInFlight x latency
+    constexpr int kInFlight = NCH == 1 ? 8 : 4;
+    for (; i + kInFlight <= cnt; i += kInFlight) {
+      float r[kInFlight][NCH][VEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kInFlight; ++u) {
         const float *row = fbase + (size_t)__shfl_sync(0xffffffffu, mine, i + u) * C;
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
@@ -121,7 +123,7 @@ vp_reduce_kernel(int N, int C, int V, const float *__restrict__ feat,
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < kInFlight; ++u)
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
 #pragma unroll
