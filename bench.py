@@ -173,7 +173,9 @@ def _pipeline_name(plan):
     sel = int(plan.desc.reserved[0])
     from sgv3d_b200 import _native as N
     blk = bool(N.lib().sgv3d_lift_splat_uses_block_pipeline(plan.desc))
-    return ("pixel-block" if blk else "voxel-tile") + (" (auto)" if sel == 0 else " (forced)")
+    from sgv3d_b200 import view_transform as VT
+    auto = sel == 0 or VT._DEFAULT_PIPELINE == VT.PIPELINE_AUTO
+    return ("pixel-block" if blk else "voxel-tile") + (" (auto policy)" if auto else " (forced)")
 
 
 def _dist():

@@ -589,13 +589,35 @@ class LiftSplat(nn.Module):
         return geometry_indices(self.frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat,
                                 reference_heights, bda_mat, self.voxel_coord, self.voxel_size, self.arith)
 
+    def _auto_pipeline(self, frames: int, channels: int, inference: bool, plan_reused: bool) -> int:
+        """AUTO policy, from the B200 measurements in profiles/README.md (round 2).  The voxel-tile pipeline is the faster
+        one for training and for large inference batches; the pixel-block pipeline (one-kernel plan, no global sort) wins
+        the small inference batches -- plan + forward 72 vs 97 us at one DAIR-R50 frame, 102 vs 189 us at one SGV3D-BSM-R50
+        frame, break-even near 8 frames (16 for the dense stride-8 maps).  With a reused plan only the forward counts: the
+        tile forward is faster on the stride-16 maps (28 vs 36 us), the block forward on the dense ones (62 vs 82 us)."""
+        if _DEFAULT_PIPELINE != PIPELINE_AUTO:
+            return _DEFAULT_PIPELINE
+        d, fh, fw = (int(v) for v in self.frustum.shape[:3])
+        # (256 x 256 and larger grids: footprints of up to 2 000 voxels per block are processed in rounds -- tile wins)
+        if not inference or channels > 96 or d > 255 or self._grid[0] * self._grid[1] > 20000:
+            return PIPELINE_TILE
+        dense = fh * fw >= 12000
+        if plan_reused:
+            return PIPELINE_BLOCK if (dense and frames <= 4) else PIPELINE_TILE
+        return PIPELINE_BLOCK if frames <= (16 if dense else 8) else PIPELINE_TILE
+
     def make_plan(self, mats_dict, sweep_index: int = 0, channels: Optional[int] = None,
-                  ctx_dtype: torch.dtype = torch.float32) -> LiftSplatPlan:
+                  ctx_dtype: torch.dtype = torch.float32, inference: bool = False,
+                  plan_reused: Optional[bool] = None) -> LiftSplatPlan:
+        """``inference``: only the forward will run on this plan (lets AUTO pick the small-batch pipeline);
+        ``plan_reused``: the plan outlives the step (defaults to ``cache_plan``)."""
         m = mats_dict
         args = (m["sensor2ego_mats"][:, sweep_index, ...], m["sensor2virtual_mats"][:, sweep_index, ...],
                 m["intrin_mats"][:, sweep_index, ...], m["ida_mats"][:, sweep_index, ...],
                 m["reference_heights"][:, sweep_index, ...], m.get("bda_mat", None))
         c = channels or self.output_channels
+        reused = self.cache_plan if plan_reused is None else plan_reused
+        pipe = self._auto_pipeline(int(args[0].shape[0]) * int(args[0].shape[1]), c, inference, reused)
         key = None
         # The cache is keyed on the identity of the calibration tensors (storage address, version counter, shape) AND
         # keeps those tensors alive next to the plan: while they live no other tensor can be allocated at their address,
@@ -603,13 +625,13 @@ class LiftSplat(nn.Module):
         # capture (a captured step must contain its own plan kernels).
         capturing = args[0].is_cuda and torch.cuda.is_current_stream_capturing()
         if self.cache_plan and not capturing:
-            key = (c, ctx_dtype, _DEFAULT_PIPELINE) + tuple(
+            key = (c, ctx_dtype, pipe) + tuple(
                 None if a is None else (a.data_ptr(), a._version, tuple(a.shape), tuple(a.stride()), a.dtype) for a in args)
             hit = self._plan_cache.get(key)
             if hit is not None:
                 return hit[0]
         plan = LiftSplatPlan(self.frustum, *args, self.voxel_coord, self.voxel_size, self._grid, c, ctx_dtype,
-                             self.arith, grid_const=self._const(args[0].device))
+                             self.arith, grid_const=self._const(args[0].device), pipeline=pipe)
         if key is not None:
             self._plan_cache = {key: (plan, args)}
         return plan
@@ -624,7 +646,8 @@ class LiftSplat(nn.Module):
         (lss_fpn.py:461).  Returns the (B, C, Y, X) contiguous BEV map of lss_fpn.py:494-495."""
         d, c = self.height_channels, self.output_channels
         hf = height_feature.float()
-        plan = self.make_plan(mats_dict, sweep_index, c)
+        inference = not (torch.is_grad_enabled() and hf.requires_grad)
+        plan = self.make_plan(mats_dict, sweep_index, c, inference=inference)
         # softmax over the D logits (lss_fpn.py:462), lift (:464-466), geometry (:478-488) and pooling
         # (:490-495) all happen inside the library, on the head's output tensor in place
         return _LiftSplatHeadFunction.apply(hf, plan, d, c)
@@ -640,7 +663,7 @@ class LiftSplat(nn.Module):
                                              or context.requires_grad)):
             # inference: softmax over the 7 semantic channels, concat and background mask (bsm_lss_fpn.py:524-529)
             # run inside the forward's context pass; the 87-channel tensor is never built
-            plan = self.make_plan(mats_dict, sweep_index, int(context.shape[1] + semantic_logits.shape[1]))
+            plan = self.make_plan(mats_dict, sweep_index, int(context.shape[1] + semantic_logits.shape[1]), inference=True)
             return plan.forward_bsm(height_logits.float(), context.float(), semantic_logits.float(), 0.45)
         c_all = int(context.shape[1] + semantic_logits.shape[1])
         if c_all <= 96 and semantic_logits.shape[1] <= 8 and context.dtype == torch.float32:
@@ -683,7 +706,8 @@ class LiftSplatGraph:
         d, c = module.height_channels, module.output_channels
         # static roadside camera (IDA deterministic, BDA identity at inference: dataset/nusc_mv_det_dataset.py:433-454):
         # the voxel-run plan is built once, outside the graph; a replay is the two forward kernels only
-        self.plan = module.make_plan(mats_dict, sweep_index, c) if static_calibration else None
+        self.plan = module.make_plan(mats_dict, sweep_index, c, inference=True, plan_reused=True) if static_calibration \
+            else None
 
         def step():
             if self.plan is not None:

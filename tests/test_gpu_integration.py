@@ -182,13 +182,17 @@ def test_patched_module_follows_a_later_load_state_dict():
     np.testing.assert_allclose(b.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
 
 
-def test_plan_cache_is_keyed_on_live_tensors_and_bypassed_under_capture():
+def test_plan_cache_is_keyed_on_live_tensors_and_bypassed_under_capture(request):
     """cache_plan must never return a plan built for other calibration values.  The cache keeps
     the keyed tensors alive (so a new tensor cannot reuse their address), sees in-place updates through the version
     counter, and is not consulted while a CUDA graph is being captured."""
     from sgv3d_b200 import LiftSplat, LiftSplatGraph
+    from sgv3d_b200 import view_transform as VT
     from sgv3d_b200.synthetic import make_activations
     shape = get_shape("small")
+    # bitwise comparisons below: both modules on the same kernel pipeline (AUTO would pick by batch and plan reuse)
+    VT.set_default_pipeline(VT.PIPELINE_TILE)
+    request.addfinalizer(lambda: VT.set_default_pipeline(VT.PIPELINE_AUTO))
     mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim, shape.downsample,
                     shape.channels, cache_plan=True).cuda()
     ref = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim, shape.downsample,
@@ -230,3 +234,35 @@ def test_plan_cache_is_keyed_on_live_tensors_and_bypassed_under_capture():
     gs.refresh_calibration(md_d)
     for k in keep:
         assert torch.equal(md_c[k], keep[k]), k
+
+
+def test_auto_pipeline_policy_and_both_choices_agree_with_the_oracle():
+    """AUTO picks the pixel-block pipeline for small inference batches and the voxel-tile pipeline for training / large
+    batches (LiftSplat._auto_pipeline, from the round-2 B200 measurements); whichever it picks, the BEV map is the oracle's."""
+    from sgv3d_b200 import LiftSplat
+    from sgv3d_b200 import view_transform as VT
+    from sgv3d_b200.synthetic import make_activations
+    shape = get_shape("small")
+    mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim, shape.downsample,
+                    shape.channels).cuda()
+    assert mod._auto_pipeline(1, 80, True, False) == VT.PIPELINE_BLOCK
+    assert mod._auto_pipeline(64, 80, True, False) == VT.PIPELINE_TILE
+    assert mod._auto_pipeline(1, 80, False, False) == VT.PIPELINE_TILE      # training
+    assert mod._auto_pipeline(1, 128, True, False) == VT.PIPELINE_TILE      # rows wider than the block pipeline supports
+    mats = make_mats(shape, 2, 1, seed=83, bda="identity")
+    md = {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).cuda(), "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).cuda(),
+          "intrin_mats": mats["intrin"].unsqueeze(1).cuda(), "ida_mats": mats["ida"].unsqueeze(1).cuda(),
+          "reference_heights": mats["reference_heights"].unsqueeze(1).cuda(), "bda_mat": mats["bda"].cuda()}
+    logits, ctx = make_activations(shape, 2, 1, seed=83)
+    hf = torch.cat((logits, ctx), 1).cuda()
+    with torch.no_grad():
+        p_inf = mod.make_plan(md, 0, shape.channels, inference=True)
+        bev_inf = mod.forward_single_sweep(hf, md)
+    p_train = mod.make_plan(md, 0, shape.channels)
+    assert p_inf.uses_block_pipeline() and not p_train.uses_block_pipeline()
+    bev_train = mod.forward_single_sweep(hf.clone().requires_grad_(True), md)
+    idx = mod.get_geometry_indices(md["sensor2ego_mats"][:, 0], md["sensor2virtual_mats"][:, 0], md["intrin_mats"][:, 0],
+                                   md["ida_mats"][:, 0], md["reference_heights"][:, 0], md["bda_mat"]).cpu().numpy()
+    want = CO.lift_splat_forward64(idx, logits.softmax(1).numpy(), ctx.numpy(), *shape.grid)
+    np.testing.assert_allclose(bev_inf.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(bev_train.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5)
