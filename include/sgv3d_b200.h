@@ -159,9 +159,9 @@ typedef struct sgv3d_lift_splat_desc {
    * lss_fpn.py:461-466, without a copy.  Within one camera the [D|C][fH][fW] block is dense. */
   int64_t height_batch_stride, ctx_batch_stride;
   int64_t grad_height_batch_stride, grad_ctx_batch_stride;
-  /* reserved[0]: kernel pipeline -- 0 auto (the pixel-block pipeline, lift_splat_block.cu, whenever it supports the
-   * shape: C <= 96, D <= 255; else the voxel-tile pipeline, lift_splat.cu), 1 voxel-tile, 2 pixel-block (error if
-   * unsupported).  Must be the same for every call that shares a workspace.  reserved[1..3]: 0. */
+  /* reserved[0]: kernel pipeline -- 0 / 1 the voxel-tile pipeline (lift_splat.cu), 2 the pixel-block pipeline
+   * (lift_splat_block.cu; C <= 96, D <= 255, error otherwise; the Python wrapper's AUTO policy picks it for small
+   * inference batches).  Must be the same for every call that shares a workspace.  reserved[1..3]: 0. */
   int32_t reserved[4];
 } sgv3d_lift_splat_desc;
 

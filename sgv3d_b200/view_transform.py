@@ -47,8 +47,10 @@ _DEFAULT_PIPELINE = PIPELINE_AUTO
 
 
 def set_default_pipeline(pipeline: int) -> None:
-    """Which kernels serve new plans: AUTO (= the voxel-tile pipeline, the faster one on B200 for every reference
-    shape), TILE, or BLOCK (the pixel-block pipeline: rows of up to 96 channels, D <= 255; error otherwise)."""
+    """Which kernels serve new plans: AUTO (LiftSplat._auto_pipeline: the pixel-block pipeline for small inference
+    batches, the voxel-tile pipeline for training and large batches -- the B200 measurements in profiles/README.md),
+    TILE, or BLOCK (the pixel-block pipeline: rows of up to 96 channels, D <= 255; error otherwise).  Plans built
+    directly with ``LiftSplatPlan(...)`` and no ``pipeline=`` argument treat AUTO as TILE."""
     global _DEFAULT_PIPELINE
     assert pipeline in (PIPELINE_AUTO, PIPELINE_TILE, PIPELINE_BLOCK)
     _DEFAULT_PIPELINE = pipeline
