@@ -137,7 +137,7 @@ bp_plan_kernel(BDims m, const float *__restrict__ u_tab, const float *__restrict
                BlockInfo *__restrict__ info, uint2 *__restrict__ ftab, int *__restrict__ alloc) {
   __shared__ geom::Camera cam;
   __shared__ int s_flags[4];   // 0: camera qualifies for the fast path, 1: z table finite, 2: hgt table valid
-  __shared__ int s_red[2][2];
+  __shared__ __align__(16) int s_red[2][2];   // (own 16 bytes: the compiler reads it with one 128-bit load)
   extern __shared__ float psm[];
   float *zs = psm;                                             // [D] height-bin values
   float *hs = psm + m.D;                                       // [D] camera height above the bin's plane
