@@ -1446,6 +1446,19 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
     acc[j] = 0.0f;
   }
   __syncthreads();  // every thread has its context row (and the exponentials are visible to the group)
+  // Per-bin gradients gbin[d][pixel] live in the context tile while it is free (between the context rows moving to
+  // registers and the g_ctx rows coming back): the run loop drops gw_r into the bins of run r, phase 4a reads them back
+  // in one uniform pass over D -- no second walk over the run table, no round trip of gw through global memory.
+  // Needs D rows of 65 floats inside the tile's Cpad rows, and pays off when the pixels have many runs (measured on
+  // B200 with every chunk on this path: SGV3D-BSM-R50, ~30 runs per pixel, 662 -> 590 us at 16 frames; DAIR-R50, ~12
+  // runs, 382 -> 388 us): taken when at least half of the chunk's pixels have 14 runs or more (block-uniform; any
+  // threshold in 12 .. 18 gives DAIR-R50 373 us, SGV3D-BSM-R50 596 us), else the run table is walked again.
+  const bool bins_in_tile = m.D <= kRowF && __syncthreads_count(cnt >= 14) >= 2 * kBwdPix;
+  float *gbin = tile;
+  if (bins_in_tile) {
+    float4 *z4 = reinterpret_cast<float4 *>(tile);
+    for (int i = tid; i < (m.D * kBwdLd + 3) / 4; i += kBwdPix * 4) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   // ---- 3a. run weights: lane l takes the runs r = l mod 4 (ascending d inside a run) ----------------------
   const size_t ell0 = ell_slot(frame_chunk, m.D, 0, tch);
@@ -1474,7 +1487,7 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
       g[k][0] = t4.x; g[k][1] = t4.y; g[k][2] = t4.z; g[k][3] = t4.w;
     }
   };
-  auto consume = [&](int r, float wr, const float (&g)[NV][4]) {
+  auto consume = [&](int r, float wr, int packed, const float (&g)[NV][4]) {
     float dot = 0.0f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -1485,19 +1498,25 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
     }
     dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 1));
     dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 2));
-    if (l == 0 && r < cnt) gw_pm[ell0 + (size_t)r * kChunk] = dot;
+    if (bins_in_tile) {
+      if (r < cnt)
+        for (int d = (packed & 0xffff) + l; d < (packed >> 16); d += 4) gbin[d * kBwdLd + px] = dot;
+    } else if (l == 0 && r < cnt) {
+      gw_pm[ell0 + (size_t)r * kChunk] = dot;
+    }
     S = __fmaf_rn(wr, dot, S);   // wr == 0 beyond the pixel's last run
   };
   for (int r0 = 0; r0 < cnt_w; r0 += 4) {
-    int vox[4];
+    int vox[4], pk[4];
     float wv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      vox[u] = 0; wv[u] = 0.0f;
+      vox[u] = 0; wv[u] = 0.0f; pk[u] = 0;
       if (r0 + u < cnt) {
         const size_t sl = ell0 + (size_t)(r0 + u) * kChunk;
         vox[u] = run_vox[sl];
         wv[u] = w_pm[sl];
+        if (bins_in_tile) pk[u] = run_d[sl];
       }
     }
 #pragma unroll
@@ -1510,24 +1529,39 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
           for (int e = 0; e < 4; ++e) { ga[k][e] = 0.0f; gb2[k][e] = 0.0f; }
         if (r0 + h < cnt) load_g(vox[h], ga);
         if (r0 + h + 1 < cnt) load_g(vox[h + 1], gb2);
-        consume(r0 + h, wv[h], ga);
-        consume(r0 + h + 1, wv[h + 1], gb2);
+        consume(r0 + h, wv[h], pk[h], ga);
+        consume(r0 + h + 1, wv[h + 1], pk[h + 1], gb2);
       }
     }
   }
-  // g_ctx row -> tile column (the context values are in registers now)
-  if (live) {
+  auto park_g_ctx = [&]() {   // g_ctx row -> tile column (the context values are in registers now)
+    if (live) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int c = l + 4 * j;
-      if (c < m.C) tile[c * kBwdLd + px] = acc[j];
+      for (int j = 0; j < NJ; ++j) {
+        const int c = l + 4 * j;
+        if (c < m.C) tile[c * kBwdLd + px] = acc[j];
+      }
     }
+  };
+  if (bins_in_tile) {
+    __syncwarp();   // the four lanes of a pixel wrote its bins
+    if (live) {
+      // ---- 4a. g_height[d] = gw[run(d)] (0 for dropped bins), or p_d (gw - S) with the fused softmax ----------
+      for (int d = l; d < m.D; d += 4) {
+        const float gv = gbin[d * kBwdLd + px];
+        col[d * kBwdPix + px] = m.logits ? __fmul_rn(__fmul_rn(col[d * kBwdPix + px], scale), __fsub_rn(gv, S)) : gv;
+      }
+    }
+    __syncthreads();  // every pixel is done with its bins: the tile takes the g_ctx rows
+    park_g_ctx();
+  } else {
+    park_g_ctx();
   }
   __syncthreads();  // tile complete; gw_pm writes of this CTA are visible to it
 
   // ---- 4a. g_height: lane l computes the bins d = l mod 4 in place of the staged column, then the block leaves as
   //          whole 256-byte rows (128-bit stores) ----------------------------------------------------------------
-  if (live) {
+  if (live && !bins_in_tile) {
     float *cp = col + px;
     auto put = [&](int d, float gv) {
       float v = gv;

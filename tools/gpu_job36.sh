@@ -1,0 +1,15 @@
+mkdir -p gpurun_out
+(timeout 2400 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 900 2>&1 | tail -12) > gpurun_out/t36_all.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench36.json 2> gpurun_out/bench36.err
+tail -4 gpurun_out/t36_all.log; tail -3 gpurun_out/bench36.err; python - <<PY
+import json
+d=json.load(open("gpurun_out/bench36.json")); r=d["roofline"]; e=d["extra"]
+print("value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"train frac",round(r["frac"],4),"fwd frac",round(r["forward_only"]["frac"],4), d["config"]["pipeline"])
+print("batch1", e["batch1_latency_us"], e["batch1_graph_latency_us"], e["batch1_static_camera_graph_latency_us"], e["frames_per_s_by_batch"])
+print("op", e["op_level_forward"])
+PY
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench36.json"))
+for s in d["extra"].get("shapes",[]): print({k:(round(v,4) if isinstance(v,float) else v) for k,v in s.items() if k in ("workload","frames","value","roofline_frac","train_roofline_frac","ms_per_step","train_ms_per_step")})
+PY
