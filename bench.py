@@ -618,6 +618,34 @@ def shape_lines(args, dev, world, barrier):
         rec["pipeline"] = _pipeline_name(plan2)
         out[key] = rec
         del plan2, m2
+    # consumer layout: the headline shape with the BEV map written / its gradient read in
+    # torch.channels_last order (same values; for a BEV trunk in that memory format).  Not the headline: the reference
+    # returns a contiguous (B, C, Y, X) map.
+    sh, nb = get_shape("dair_r50"), 64
+    m3 = LiftSplat(sh.x_bound, sh.y_bound, sh.z_bound, sh.d_bound, sh.final_dim, sh.downsample, sh.channels,
+                   bev_channels_last=True).to(dev)
+    md3 = _mats_dict(make_mats(sh, nb, 1, seed=78 + 1000 * rank, bda="identity"), dev)
+    lg3, cx3 = make_activations(sh, nb, 1, seed=78 + 1000 * rank, device=dev, generator_device=dev)
+    hf3 = torch.cat((lg3, cx3), 1).contiguous()
+    fb3, bb3 = sh.fused_forward_bytes(4) * nb, sh.fused_backward_bytes(4) * nb
+    g3 = LiftSplatGraph(m3, hf3, md3, warmup=1)
+    ms_f = timed(g3)
+    del g3
+    plan3 = m3.make_plan(md3, 0, sh.channels)
+    gb3 = torch.randn(nb, sh.channels, sh.grid[1], sh.grid[0], device=dev).contiguous(memory_format=torch.channels_last)
+
+    def tstep3():
+        plan3.rebuild()
+        plan3.forward(hf3[:, :sh.D], hf3[:, sh.D:], logits=True)
+        plan3.backward(gb3, hf3[:, :sh.D], hf3[:, sh.D:], logits=True)
+    ms_t = timed(tstep3)
+    out["dair_r50_b64_f32_bev_channels_last"] = {
+        "frames_per_gpu": nb, "n_gpus": world, "ctx_dtype": "float32", "bev_memory_format": "torch.channels_last",
+        "forward_step": {"ms": ms_f, "frames_per_s": world * nb / (ms_f * 1e-3), "frac_of_measured_peak": fb3 / ms_f / 1e6 / peak},
+        "train_step": {"ms": ms_t, "frames_per_s": world * nb / (ms_t * 1e-3), "algorithmic_bytes_per_gpu": fb3 + bb3,
+                       "achieved_GBs_per_gpu": (fb3 + bb3) / ms_t / 1e6, "frac_of_measured_peak": (fb3 + bb3) / ms_t / 1e6 / peak},
+        "pipeline": _pipeline_name(plan3)}
+    del plan3, m3
     return out
 
 

@@ -161,7 +161,12 @@ typedef struct sgv3d_lift_splat_desc {
   int64_t grad_height_batch_stride, grad_ctx_batch_stride;
   /* reserved[0]: kernel pipeline -- 0 / 1 the voxel-tile pipeline (lift_splat.cu), 2 the pixel-block pipeline
    * (lift_splat_block.cu; C <= 96, D <= 255, error otherwise; the Python wrapper's AUTO policy picks it for small
-   * inference batches).  Must be the same for every call that shares a workspace.  reserved[1..3]: 0. */
+   * inference batches).  Must be the same for every call that shares a workspace.
+   * reserved[1]: memory layout of the BEV map -- 0: (B, C, Y, X) contiguous, what lss_fpn.py:494-495 returns; 2: the same
+   * logical tensor in channels-last memory order (b, y, x, c), i.e. torch.channels_last strides, for a BEV trunk that runs
+   * its convolutions in that format: `bev` of sgv3d_lift_splat_forward is written and `grad_bev` of
+   * sgv3d_lift_splat_backward is read in that order (no transposed copies on either side).  Voxel-tile pipeline,
+   * C in {16, 32, ..., 96}, 16-byte aligned pointers; error otherwise.  reserved[2..3]: 0. */
   int32_t reserved[4];
 } sgv3d_lift_splat_desc;
 

@@ -70,7 +70,8 @@ struct Workspace {
   size_t bytes;
 };
 
-RowPerm row_perm(const Dims &m) { return RowPerm{m.G == 4 ? 2 : (m.G == 8 ? 3 : 4), m.Cpad}; }
+// (channels-last BEV map: the context rows keep the natural channel order -- the reduce writes them out as they are)
+RowPerm row_perm(const Dims &m) { return RowPerm{m.cl ? 0 : (m.G == 4 ? 2 : (m.G == 8 ? 3 : 4)), m.Cpad}; }
 
 Workspace carve(void *ws, const Dims &m, int ctx_dtype) {
   Workspace w;
@@ -973,6 +974,17 @@ struct StreamAcc {
       }
   }
   // partial sum of a voxel that an earlier stream started: parked per stream, added by that stream later
+  // channels-last output: the sums ARE the voxel's row (natural channel order: vector k of lane l = channels
+  // 4*(k*G + l) ..+3) of the [voxel][C] shared-memory tile; the G lanes of a vector cover G*16 contiguous bytes.  Then clear.
+  __device__ __forceinline__ void flush_row(float *row, int l, int C) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = 4 * (k * G + l);
+      if (c4 < C) *reinterpret_cast<float4 *>(row + c4) = make_float4(a[k][0], a[k][1], a[k][2], a[k][3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[k][e] = 0.0f;
+    }
+  }
   __device__ __forceinline__ void store_head(float *head /*[4*G*NV] of this stream*/, int l) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -1004,11 +1016,28 @@ __device__ __forceinline__ Entry load_entry(const Entry *__restrict__ ent, int j
 
 // One stream = one G-lane group walking the slice [j0, j1) of the tile's sorted entries, two entries in
 // flight.
-template <typename CT, int G, int NV, bool STAGED>
+// CL: channels-last output -- a finished voxel is a row of the [voxel][C] shared-memory tile (which then leaves as ONE
+// contiguous block: the rows of a tile's voxels are adjacent in a (b, y, x, c) map); otherwise a column of the swizzled
+// [channel][voxel] tile.
+struct ClOut {
+  float *rows;  // row of voxel 0 of the tile (shared memory)
+  int C;
+};
+template <int G, int NV, bool CL>
+__device__ __forceinline__ void flush_voxel(StreamAcc<G, NV> &acc, unsigned tile_lane, int l, unsigned box_bytes, int vt,
+                                            const ClOut &cl) {
+  if (CL) {
+    acc.flush_row(cl.rows + vt * cl.C, l, cl.C);
+  } else {
+    acc.flush_tile(tile_lane, l, box_bytes, vt);
+  }
+}
+
+template <typename CT, int G, int NV, bool STAGED, bool CL>
 __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, bool &head,
                                             const Entry *__restrict__ ent, int tile_lo, int j0, int j1,
                                             const unsigned char *__restrict__ lane_rows, unsigned tile_lane,
-                                            float *my_head, int l, unsigned box_bytes) {
+                                            float *my_head, int l, unsigned box_bytes, const ClOut &cl) {
   constexpr unsigned kRowBytes = 4 * G * NV * sizeof(CT);
   auto load_row = [&](const Entry &en, float (&r)[NV][4]) {
     const unsigned char *row = lane_rows + (size_t)(en.off >> 6) * kRowBytes;
@@ -1020,7 +1049,7 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
     if (vt != cur) {
       if (cur >= 0) {
         if (head) acc.store_head(my_head, l);
-        else acc.flush_tile(tile_lane, l, box_bytes, cur);
+        else flush_voxel<G, NV, CL>(acc, tile_lane, l, box_bytes, cur, cl);
         head = false;
       }
       cur = vt;
@@ -1067,7 +1096,10 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
 //   3. finished voxel sums go to a swizzled [channel][voxel] tile, and the tile leaves as 128-byte row
 //      segments of the NCHW planes (fully coalesced, every output byte written exactly once).
 // ---------------------------------------------------------------------------------------------
-template <typename CT, int G, int NV, int NSTR>
+//   CL (channels-last BEV map, desc.reserved[1] bit 1): the tile is [voxel][C] rows instead, a finished voxel's sums
+//      are one row of it, and the tile -- 64 adjacent rows of the (b, y, x, c) map, one contiguous block of memory --
+//      leaves with a single bulk-async (TMA) shared -> global copy.
+template <typename CT, int G, int NV, int NSTR, bool CL>
 __global__ void __launch_bounds__(NSTR * G)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ tile_ptr,
                  const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out, int stage_cap) {
@@ -1086,14 +1118,19 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
   const int nv = min(kTileV, m.V - v0);
   const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1) + blockIdx.x;
   const int tile_lo = __ldg(tp), tile_hi = __ldg(tp + 1);
-  float *out = bev + (size_t)b * m.C * m.V + v0;
+  float *out = bev + (size_t)b * m.C * m.V + (CL ? (size_t)v0 * m.C : (size_t)v0);
+  ClOut cl;
+  cl.rows = reinterpret_cast<float *>(tile); cl.C = m.C;   // (64 * C floats <= the 2 * Cpad * 32 of the NCHW tile)
 
   // thread <-> (channel row c0 + kThreads/16 * i, 16-byte chunk q) of the tile for the copy-out loops
   constexpr int kRowStep = kThreads / 16;
   static_assert(kRowStep % 8 == 0, "copy-out relies on (row & 7) being loop invariant");
   const int q = tid & 15, c0 = tid >> 4;
   if (tile_hi == tile_lo) {  // no point falls into this tile: zero fill
-    if (vec_out) {
+    if (CL) {  // the tile's rows are one contiguous range of nv * C floats (C % 4 == 0, 16-byte aligned)
+      for (int i = tid; i < nv * (m.C >> 2); i += kThreads)
+        stg_stream_f4(reinterpret_cast<float4 *>(out) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    } else if (vec_out) {
       if (4 * q < nv) {
         float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)c0 * m.V) + q;
         const size_t step = (size_t)(kRowStep / 4) * m.V;  // kRowStep channel rows, in float4 units
@@ -1113,7 +1150,7 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
   const Entry *ent = vm_ent + (size_t)b * m.cap;
   if (staged)
     for (int i = tid; i < n_t; i += kThreads) cp_async_8(s_ent + i, ent + tile_lo + i);
-  for (int i = tid; i < 2 * (int)kBoxBytes / 16; i += kThreads)
+  for (int i = tid; i < (CL ? kTileV * m.C / 4 : 2 * (int)kBoxBytes / 16); i += kThreads)
     reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   cp_async_wait_all();
   __syncthreads();
@@ -1132,9 +1169,9 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
   bool head = false;    // the segment being accumulated continues a voxel started by an earlier stream
   const Entry *se = s_ent - tile_lo;  // staged entries, addressed like the plan's
   if (staged)
-    stream_loop<CT, G, NV, true>(acc, cur, head, se, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes);
+    stream_loop<CT, G, NV, true, CL>(acc, cur, head, se, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes, cl);
   else
-    stream_loop<CT, G, NV, false>(acc, cur, head, ent, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes);
+    stream_loop<CT, G, NV, false, CL>(acc, cur, head, ent, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes, cl);
   // voxel (in tile) of entry j
   auto vox_at = [&](int j) -> int {
     return (int)((staged ? load_entry<true>(se, j) : load_entry<false>(ent, j)).off & 63u);
@@ -1143,7 +1180,7 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
   bool tail = false;
   if (cur >= 0) {
     if (head) acc.store_head(my_head, l);                 // the whole slice lies inside one earlier voxel
-    else if (j1 == tile_hi || vox_at(j1) != cur) acc.flush_tile(tile_lane, l, kBoxBytes, cur);
+    else if (j1 == tile_hi || vox_at(j1) != cur) flush_voxel<G, NV, CL>(acc, tile_lane, l, kBoxBytes, cur, cl);
     else tail = true;                                      // later slices continue this voxel
   }
   __syncthreads();
@@ -1154,9 +1191,22 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
       if (jk >= tile_hi || vox_at(jk) != cur) break;
       acc.add_head(s_head + k * kRows, l);
     }
-    acc.flush_tile(tile_lane, l, kBoxBytes, cur);
+    flush_voxel<G, NV, CL>(acc, tile_lane, l, kBoxBytes, cur, cl);
   }
   __syncthreads();
+  if (CL) {
+    // one bulk-async copy moves the whole tile (nv * C * 4 bytes, a multiple of 16): the generic-proxy writes above are
+    // ordered before the async proxy's reads by the fence, and the CTA may retire once the engine has READ shared memory
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(smem_u32(tile)),
+                   "r"((unsigned)(nv * m.C * (int)sizeof(float)))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
 
   // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line.
   // Rows advance by a multiple of 8 per step, so (row & 7) and with it the swizzled chunk position never change.
@@ -1329,7 +1379,7 @@ ls_grad_rows_kernel(Dims m, const float *__restrict__ grad_bev, const int *__res
 constexpr int kBwdPix = 64;    // pixels per CTA (half a plan chunk)
 constexpr int kBwdLd = kBwdPix + 1;
 
-template <typename CT, int NV, int OCC, bool BSM>
+template <typename CT, int NV, int OCC, bool BSM, bool NAT>
 __global__ void __launch_bounds__(kBwdPix * 4, OCC)
 ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, int vec16_out,
                          const CT *__restrict__ context, BsmAssembly bsm, float *__restrict__ g_semantic,
@@ -1438,11 +1488,14 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
     scale = __fdiv_rn(1.0f, sm);
   }
   // context row of the pixel -> registers (channel l + 4j)
+  // channel held in slot j of lane l: l + 4j in the permuted rows ls_grad_rows_kernel writes; 16 (j / 4) + 4 l + j % 4
+  // when the rows are the caller's channels-last gradient itself (NAT: natural order, row stride C = 16 NV)
+  auto chan = [&](int j) { return NAT ? 16 * (j >> 2) + 4 * l + (j & 3) : l + 4 * j; };
   float cx[NJ], acc[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const int c = l + 4 * j;
-    cx[j] = (live && c < m.C) ? tile[c * kBwdLd + px] : 0.0f;
+    const int c = chan(j);
+    cx[j] = (live && (NAT || c < m.C)) ? tile[c * kBwdLd + px] : 0.0f;   // (NAT: C = 16 NV, every slot is a channel)
     acc[j] = 0.0f;
   }
   __syncthreads();  // every thread has its context row (and the exponentials are visible to the group)
@@ -1476,11 +1529,12 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
   // Run descriptors are fetched four ahead and two gradient rows are in flight per group, so that the
   // descriptor -> row dependency and the row latency overlap with the arithmetic of earlier runs.
   // The trip count is warp-uniform (longest pixel of the warp) so that the butterflies use the full mask.
-  const float *gb = gT + (size_t)b * m.V * kRowF + 4 * l;
+  constexpr int g_stride = kRowF;   // (NAT: the caller's rows have C = 16 NV = kRowF floats as well)
+  const float *gb = gT + (size_t)b * m.V * g_stride + 4 * l;
   const int cnt_w = __reduce_max_sync(0xffffffffu, cnt);
   float S = 0.0f;
   auto load_g = [&](int vox, float (&g)[NV][4]) {
-    const float *grow = gb + (size_t)vox * kRowF;
+    const float *grow = gb + (size_t)vox * g_stride;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const float4 t4 = __ldg(reinterpret_cast<const float4 *>(grow + 16 * k));
@@ -1538,8 +1592,8 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
     if (live) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const int c = l + 4 * j;
-        if (c < m.C) tile[c * kBwdLd + px] = acc[j];
+        const int c = chan(j);
+        if (NAT || c < m.C) tile[c * kBwdLd + px] = acc[j];
       }
     }
   };
@@ -1688,11 +1742,18 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   int stage_cap = 1536;
   while (stage_cap < 2 * expect && stage_cap < 6144) stage_cap += 1536;
   const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * stage_cap;
-  if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR>, smem)) return rc;
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
-  ls_reduce_kernel<CT, G, NV, NSTR><<<grid, NSTR * G, smem, s>>>(
-      m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+  if (m.cl) {
+    SGV3D_REQUIRE(reinterpret_cast<uintptr_t>(bev) % 16 == 0, "lift_splat_forward: channels-last BEV map must be 16-byte aligned");
+    if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, true>, smem)) return rc;
+    ls_reduce_kernel<CT, G, NV, NSTR, true><<<grid, NSTR * G, smem, s>>>(
+        m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+  } else {
+    if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, false>, smem)) return rc;
+    ls_reduce_kernel<CT, G, NV, NSTR, false><<<grid, NSTR * G, smem, s>>>(
+        m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+  }
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
 }
@@ -1739,14 +1800,21 @@ int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *he
 #define SGV3D_BWD_CHUNK(OCC)                                                                                   \
   do {                                                                                                         \
     if (bsm.sem) {                                                                                             \
-      if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, true>, smem)) return rc;                     \
-      ls_backward_chunk_kernel<CT, NV, OCC, true><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(         \
+      if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, true, false>, smem)) return rc;              \
+      ls_backward_chunk_kernel<CT, NV, OCC, true, false><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(  \
           m, height, vec16, vec16_out, static_cast<const CT *>(context), bsm, grad_semantic, w.gT, w.run_cnt,  \
           w.run_vox, w.run_d, w.w_pm, w.gw_pm, grad_height, grad_context);                                     \
       break;                                                                                                   \
     }                                                                                                          \
-    if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, false>, smem)) return rc;                      \
-    ls_backward_chunk_kernel<CT, NV, OCC, false><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(          \
+    if (m.cl) {                                                                                                \
+      if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, false, true>, smem)) return rc;              \
+      ls_backward_chunk_kernel<CT, NV, OCC, false, true><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(  \
+          m, height, vec16, vec16_out, static_cast<const CT *>(context), bsm, grad_semantic, w.gT, w.run_cnt,  \
+          w.run_vox, w.run_d, w.w_pm, w.gw_pm, grad_height, grad_context);                                     \
+      break;                                                                                                   \
+    }                                                                                                          \
+    if (int rc = set_smem(ls_backward_chunk_kernel<CT, NV, OCC, false, false>, smem)) return rc;               \
+    ls_backward_chunk_kernel<CT, NV, OCC, false, false><<<dim3(2 * m.nchunks, m.B), kBwdPix * 4, smem, s>>>(   \
         m, height, vec16, vec16_out, static_cast<const CT *>(context), bsm, grad_semantic, w.gT, w.run_cnt,    \
         w.run_vox, w.run_d, w.w_pm, w.gw_pm, grad_height, grad_context);                                       \
   } while (0)
@@ -1813,14 +1881,21 @@ int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, cons
                           const float *height, const void *context, float *grad_height, float *grad_context,
                           cudaStream_t s, BsmAssembly bsm = BsmAssembly{nullptr, 0, 0, 0.0f},
                           float *grad_semantic = nullptr) {
-  // grad_bev -> one row per voxel, then everything else per pixel chunk in one kernel
-  const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
-  if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
-  ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
-  SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
+  // grad_bev -> one row per voxel, then everything else per pixel chunk in one kernel.  A channels-last gradient
+  // (m.cl) already IS one row per voxel: the chunk kernel gathers from it directly, no copy.
+  Workspace wg = w;
+  if (m.cl) {
+    SGV3D_REQUIRE(reinterpret_cast<uintptr_t>(grad_bev) % 16 == 0, "lift_splat_backward: channels-last grad_bev must be 16-byte aligned");
+    wg.gT = const_cast<float *>(grad_bev);   // (read only by the chunk kernel)
+  } else {
+    const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
+    if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
+    ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
+    SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
+  }
   return ctx_dtype == SGV3D_DTYPE_BF16
-             ? launch_backward_chunk<__nv_bfloat16>(m, w, height, context, grad_height, grad_context, s)
-             : launch_backward_chunk<float>(m, w, height, context, grad_height, grad_context, s, bsm, grad_semantic);
+             ? launch_backward_chunk<__nv_bfloat16>(m, wg, height, context, grad_height, grad_context, s)
+             : launch_backward_chunk<float>(m, wg, height, context, grad_height, grad_context, s, bsm, grad_semantic);
 }
 
 // Which pipeline serves this descriptor: desc->reserved[0] = 0 (auto), 1 (voxel-tile pipeline of this file),
@@ -1838,6 +1913,9 @@ void *block_ws(void *workspace, const Dims &m, int ctx_dtype) {
 int check_pipeline(const sgv3d_lift_splat_desc *desc, const Dims &m, const char *who) {
   SGV3D_REQUIRE(desc->reserved[0] >= 0 && desc->reserved[0] <= 2, "%s: bad pipeline selector %d", who, desc->reserved[0]);
   SGV3D_REQUIRE(desc->reserved[0] != 2 || block::supported(m), "%s: the pixel-block pipeline does not support this shape", who);
+  SGV3D_REQUIRE((desc->reserved[1] & ~2) == 0, "%s: reserved[1] = %d", who, desc->reserved[1]);
+  SGV3D_REQUIRE(!m.cl || (desc->reserved[0] != 2 && m.C % 16 == 0 && m.C <= 96),
+                "%s: the channels-last BEV layout needs the voxel-tile pipeline and C in {16, 32, ..., 96}", who);
   return SGV3D_OK;
 }
 geom::Grid make_grid(const Dims &m, const float *lower3, const float *size3) {
@@ -2046,6 +2124,7 @@ extern "C" int sgv3d_lift_splat_backward_bsm(const sgv3d_lift_splat_desc *desc, 
   SGV3D_REQUIRE(semantic_batch_stride >= 0, "lift_splat_backward_bsm: negative batch stride");
   Dims m = make_dims(desc);
   SGV3D_REQUIRE(!use_block(desc, m), "lift_splat_backward_bsm: voxel-tile pipeline only");
+  SGV3D_REQUIRE(desc->reserved[1] == 0, "lift_splat_backward_bsm: NCHW BEV gradient only");
   const int Cc = m.C - semantic_channels;
   // `context` / `grad_context` hold the C - Cs feature channels: their dense camera blocks are that much smaller
   if (!desc->ctx_batch_stride) m.cs = (long long)Cc * m.P;

@@ -23,6 +23,7 @@ struct Dims {
   int cap;      // max runs per frame (= ELL slots per frame)
   int ntiles;   // ceil(V / 64) reduce tiles per frame
   int logits;             // height tensor holds raw logits (softmax over D fused)
+  int cl;                 // BEV map / its gradient are channels-last in memory: (b, y, x, c) (desc.reserved[1] bit 1)
   long long hs, cs;       // element strides between consecutive cameras of height / context
   long long ghs, gcs;     // same for grad_height / grad_context
 };
@@ -49,6 +50,7 @@ inline Dims make_dims(const sgv3d_lift_splat_desc *d) {
   m.cap = m.nchunks * kChunk * m.D;
   m.ntiles = ceil_div(m.V, 64);
   m.logits = d->height_is_logits;
+  m.cl = (d->reserved[1] & 2) ? 1 : 0;
   m.hs = d->height_batch_stride ? d->height_batch_stride : (long long)m.D * m.P;
   m.cs = d->ctx_batch_stride ? d->ctx_batch_stride : (long long)m.C * m.P;
   m.ghs = d->grad_height_batch_stride ? d->grad_height_batch_stride : (long long)m.D * m.P;

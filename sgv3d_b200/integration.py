@@ -94,10 +94,12 @@ def _sync_buffers(backbone) -> None:
         object.__setattr__(backbone, "_sgv3d_buffer_sig", sig)
 
 
-def patch_view_transform(backbone, arith=None, cache_plan: bool = False, is_bsm=None):
+def patch_view_transform(backbone, arith=None, cache_plan: bool = False, is_bsm=None, bev_channels_last: bool = False):
     """Rebind ``backbone._forward_single_sweep`` to the fused path.  ``cache_plan=True`` re-uses the voxel-run plan
     while the calibration tensors are unchanged (static roadside camera, inference).  ``is_bsm`` overrides the
-    structural LSSFPN / BSMLSSFPN detection."""
+    structural LSSFPN / BSMLSSFPN detection.  ``bev_channels_last=True`` (LSSFPN, 16 .. 96 channels) returns the BEV
+    map with ``torch.channels_last`` strides -- same shape and values -- for a BEV trunk converted to that memory
+    format; forward and backward then skip their layout copies."""
     if not _base_voxel_net_hook(backbone):
         raise RuntimeError(f"{type(backbone).__name__} overrides _forward_voxel_net: the fused path never builds the "
                            "frustum tensor that hook transforms; refusing to patch")
@@ -105,7 +107,8 @@ def patch_view_transform(backbone, arith=None, cache_plan: bool = False, is_bsm=
         if not hasattr(backbone, name):
             raise RuntimeError(f"{type(backbone).__name__} has no attribute {name!r}: not an LSSFPN-like module")
     ls = LiftSplat.from_buffers(backbone.frustum, backbone.voxel_coord, backbone.voxel_size, backbone.voxel_num,
-                                backbone.output_channels, arith=arith, cache_plan=cache_plan)
+                                backbone.output_channels, arith=arith, cache_plan=cache_plan,
+                                bev_channels_last=bev_channels_last)
     ls = ls.to(backbone.frustum.device)
     # plain attribute (not a registered sub-module): the state_dict of the reference module is unchanged
     object.__setattr__(backbone, "_sgv3d_lift_splat", ls)
@@ -115,6 +118,8 @@ def patch_view_transform(backbone, arith=None, cache_plan: bool = False, is_bsm=
                        tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in
                              (backbone.frustum, backbone.voxel_coord, backbone.voxel_size, backbone.voxel_num)))
     bsm = _is_bsm(backbone) if is_bsm is None else bool(is_bsm)
+    if bsm and bev_channels_last:
+        raise RuntimeError("bev_channels_last: LSSFPN call site only (the 87-channel BSM map stays (B, C, Y, X) contiguous)")
     fn = _bsm_single_sweep if bsm else _lssfpn_single_sweep
     object.__setattr__(backbone, "_forward_single_sweep", types.MethodType(fn, backbone))
     return backbone

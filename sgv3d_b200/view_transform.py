@@ -283,7 +283,8 @@ class LiftSplatPlan:
     def __init__(self, frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
                  bda_mat, voxel_coord, voxel_size, voxel_num: Sequence[int], channels: int,
                  ctx_dtype: torch.dtype = torch.float32, arith: Optional[int] = None,
-                 grid_const: Optional[_GridConst] = None, pipeline: Optional[int] = None):
+                 grid_const: Optional[_GridConst] = None, pipeline: Optional[int] = None,
+                 channels_last: bool = False):
         g = _Geometry(frustum, sensor2ego_mat, sensor2virtual_mat, intrin_mat, ida_mat, reference_heights,
                       bda_mat, voxel_coord, voxel_size, grid_const)
         self.geometry = g
@@ -296,6 +297,11 @@ class LiftSplatPlan:
                                     arith=default_arith() if arith is None else arith,
                                     ctx_dtype=N.DTYPE_BF16 if ctx_dtype == torch.bfloat16 else N.DTYPE_F32)
         self.desc.reserved[0] = _DEFAULT_PIPELINE if pipeline is None else pipeline
+        # BEV map (and the gradient the backward reads) in torch.channels_last memory order -- same logical
+        # (B, C, Y, X) tensor, no transposed copy on either side (include/sgv3d_b200.h: reserved[1] = 2)
+        self.channels_last = bool(channels_last)
+        if self.channels_last and (int(channels) % 16 != 0 or int(channels) > 96 or self.desc.reserved[0] == PIPELINE_BLOCK):
+            raise RuntimeError("channels_last BEV maps need the voxel-tile pipeline and 16, 32, ..., 96 channels")
         L = N.lib()
         self.ws_bytes = L.sgv3d_lift_splat_workspace_bytes(self.desc)
         if g.B > 0 and self.ws_bytes == 0:
@@ -330,6 +336,7 @@ class LiftSplatPlan:
         self._check_inputs(height, context)
         c = N.LiftSplatDesc.from_buffer_copy(d)
         c.height_is_logits = 1 if logits else 0
+        c.reserved[1] = 2 if self.channels_last else 0
         c.height_batch_stride = _camera_block_stride(height, d.D, d.fH, d.fW, "height")
         c.ctx_batch_stride = _camera_block_stride(context, d.C, d.fH, d.fW, "context")
         if g_height is not None:
@@ -341,7 +348,8 @@ class LiftSplatPlan:
     def forward(self, height: torch.Tensor, context: torch.Tensor, logits: bool = False) -> torch.Tensor:
         """``height``: probabilities (or raw logits with ``logits=True``: the softmax over D is fused)."""
         d = self._call_desc(height, context, logits)
-        bev = torch.empty(d.B, d.C, d.Y, d.X, dtype=torch.float32, device=self.device)
+        bev = torch.empty(d.B, d.C, d.Y, d.X, dtype=torch.float32, device=self.device,
+                          memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
         with torch.cuda.device(self.device):
             N.check(N.lib().sgv3d_lift_splat_forward(d, N.ptr(height), N.ptr(context), N.ptr(bev), N.ptr(self.ws),
                                                      self.ws_bytes, N.current_stream()))
@@ -357,6 +365,8 @@ class LiftSplatPlan:
         cc = d.C - cs
         if self.ctx_dtype != torch.float32:
             raise RuntimeError("forward_bsm: float32 context only")
+        if self.channels_last:
+            raise RuntimeError("forward_bsm: contiguous (B, C, Y, X) BEV maps only")
         for name, t, ch in (("height", height, d.D), ("context", context, cc), ("semantic_logits", semantic_logits, cs)):
             if not t.is_cuda or t.dtype != torch.float32:
                 raise RuntimeError(f"forward_bsm: {name} must be a float32 CUDA tensor")
@@ -410,7 +420,10 @@ class LiftSplatPlan:
                  out_height: Optional[torch.Tensor] = None, out_context: Optional[torch.Tensor] = None):
         """Gradients w.r.t. ``height`` (w.r.t. the logits when ``logits=True``) and ``context``; optionally
         written straight into caller-provided (possibly strided) buffers."""
-        g = grad_bev.float().contiguous()
+        # (a channels_last plan reads the gradient in channels_last order: no copy when the BEV trunk's backward
+        # produced it that way, which it does when it consumed the channels_last map)
+        g = grad_bev.float().contiguous(memory_format=torch.channels_last if self.channels_last
+                                        else torch.contiguous_format)
         d0 = self.desc
         assert tuple(g.shape) == (d0.B, d0.C, d0.Y, d0.X)
         bn = d0.B * d0.Nc
@@ -526,8 +539,13 @@ class LiftSplat(nn.Module):
     ``_forward_single_sweep`` returns for the BEV map (lss_fpn.py:494-495)."""
 
     def __init__(self, x_bound, y_bound, z_bound, d_bound, final_dim, downsample_factor, output_channels,
-                 is_bsm: bool = False, arith: Optional[int] = None, cache_plan: bool = False):
+                 is_bsm: bool = False, arith: Optional[int] = None, cache_plan: bool = False,
+                 bev_channels_last: bool = False):
         super().__init__()
+        # True: the BEV map is returned with torch.channels_last strides (same values, same shape) for a BEV trunk
+        # that runs in that memory format, and its gradient is consumed in that order -- the forward's transpose
+        # through shared memory and the backward's gradient-row copy disappear (LSSFPN call site, 16 .. 96 channels)
+        self.bev_channels_last = bool(bev_channels_last) and not is_bsm
         # BSMLSSFPN halves the stride of the lifted feature map (bsm_lss_fpn.py:343)
         self.downsample_factor = downsample_factor // 2 if is_bsm else downsample_factor
         self.is_bsm = is_bsm
@@ -549,7 +567,8 @@ class LiftSplat(nn.Module):
 
     @classmethod
     def from_buffers(cls, frustum, voxel_coord, voxel_size, voxel_num, output_channels: int,
-                     arith: Optional[int] = None, cache_plan: bool = False) -> "LiftSplat":
+                     arith: Optional[int] = None, cache_plan: bool = False,
+                     bev_channels_last: bool = False) -> "LiftSplat":
         """Build the view transform around the four buffers an existing ``LSSFPN`` / ``BSMLSSFPN`` already
         registered (lss_fpn.py:281-293), so that the very same fp32 values enter the kernels."""
         self = cls.__new__(cls)
@@ -561,6 +580,7 @@ class LiftSplat(nn.Module):
         self.output_channels = int(output_channels)
         self.arith = arith
         self.cache_plan = cache_plan
+        self.bev_channels_last = bool(bev_channels_last)
         self.register_buffer("voxel_size", voxel_size.detach().clone().float())
         self.register_buffer("voxel_coord", voxel_coord.detach().clone().float())
         self.register_buffer("voxel_num", voxel_num.detach().clone().long())
@@ -601,7 +621,7 @@ class LiftSplat(nn.Module):
             return _DEFAULT_PIPELINE
         d, fh, fw = (int(v) for v in self.frustum.shape[:3])
         # (256 x 256 and larger grids: footprints of up to 2 000 voxels per block are processed in rounds -- tile wins)
-        if not inference or channels > 96 or d > 255 or self._grid[0] * self._grid[1] > 20000:
+        if not inference or channels > 96 or d > 255 or self._grid[0] * self._grid[1] > 20000 or self.bev_channels_last:
             return PIPELINE_TILE
         dense = fh * fw >= 12000
         if plan_reused:
@@ -627,13 +647,14 @@ class LiftSplat(nn.Module):
         # capture (a captured step must contain its own plan kernels).
         capturing = args[0].is_cuda and torch.cuda.is_current_stream_capturing()
         if self.cache_plan and not capturing:
-            key = (c, ctx_dtype, pipe) + tuple(
+            key = (c, ctx_dtype, pipe, self.bev_channels_last) + tuple(
                 None if a is None else (a.data_ptr(), a._version, tuple(a.shape), tuple(a.stride()), a.dtype) for a in args)
             hit = self._plan_cache.get(key)
             if hit is not None:
                 return hit[0]
         plan = LiftSplatPlan(self.frustum, *args, self.voxel_coord, self.voxel_size, self._grid, c, ctx_dtype,
-                             self.arith, grid_const=self._const(args[0].device), pipeline=pipe)
+                             self.arith, grid_const=self._const(args[0].device), pipeline=pipe,
+                             channels_last=self.bev_channels_last and c == self.output_channels)
         if key is not None:
             self._plan_cache = {key: (plan, args)}
         return plan

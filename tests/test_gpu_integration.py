@@ -266,3 +266,92 @@ def test_auto_pipeline_policy_and_both_choices_agree_with_the_oracle():
     want = CO.lift_splat_forward64(idx, logits.softmax(1).numpy(), ctx.numpy(), *shape.grid)
     np.testing.assert_allclose(bev_inf.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(bev_train.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("channels", [16, 48, 80, 96])
+def test_channels_last_bev_map_and_gradient(channels):
+    """reserved[1] = 2: the BEV map is written, and its gradient read, in torch.channels_last memory order (SURVEY 8f
+    row 4, consumer layout).  Same logical tensor: forward values and g_context bitwise equal to the (B, C, Y, X)
+    contiguous path (same summation orders), g_height within tolerance (the 4-lane dot product sums the channels in
+    another order), everything within tolerance of the fp64 oracle."""
+    from oracle import c_oracle as CO
+    from oracle import lift_splat_oracle as O
+    from sgv3d_b200 import view_transform as VT
+    from sgv3d_b200.synthetic import make_activations
+    from tests.helpers import frustum_axes, oracle_frustum
+    shape = get_shape("small")
+    B = 3
+    mats = make_mats(shape, B, 1, seed=70 + channels, bda="identity")
+    fr = oracle_frustum(shape)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    dev = {k: v.cuda() for k, v in mats.items()}
+    args = (fr, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"], dev["reference_heights"], dev["bda"],
+            vc, vs, shape.grid, channels)
+    plan = VT.LiftSplatPlan(*args, arith=0, pipeline=VT.PIPELINE_TILE)
+    plan_cl = VT.LiftSplatPlan(*args, arith=0, pipeline=VT.PIPELINE_TILE, channels_last=True)
+    logits, ctx = make_activations(shape, B, 1, seed=channels, channels=channels)
+    lg, cg = logits.cuda(), ctx.cuda()
+    bev = plan.forward(lg, cg, logits=True)
+    bev_cl = plan_cl.forward(lg, cg, logits=True)
+    assert bev_cl.shape == bev.shape and bev_cl.is_contiguous(memory_format=torch.channels_last)
+    assert not bev_cl.is_contiguous() and torch.equal(bev_cl, bev)
+    gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(channels))
+    g_h, g_c = plan.backward(gb.cuda(), lg, cg, logits=True)
+    for g_in in (gb.cuda().contiguous(memory_format=torch.channels_last), gb.cuda()):   # no-copy and converting input
+        g_h2, g_c2 = plan_cl.backward(g_in, lg, cg, logits=True)
+        assert torch.equal(g_c2, g_c)
+        torch.testing.assert_close(g_h2, g_h, rtol=1e-4, atol=1e-5)
+    # against the oracle
+    ida_inv, mv, me = O.camera_matrices(dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"])
+    u, v, z = (t.numpy() for t in frustum_axes(fr))
+    xyz = CO.geometry(0, u, v, z, ida_inv.cpu().numpy(), mv.cpu().numpy(), me.cpu().numpy(),
+                      mats["reference_heights"].numpy(), mats["bda"].numpy())
+    idx = CO.quantize(xyz, (vc - vs / 2.0).numpy(), vs.numpy())
+    height = logits.softmax(1)
+    want = CO.lift_splat_forward64(idx, height.numpy(), ctx.numpy(), *shape.grid)
+    np.testing.assert_allclose(bev_cl.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    g_hp, g_cp = plan_cl.backward(gb.cuda(), height.cuda(), cg)          # probabilities in: d/d height
+    gh64, gc64 = CO.lift_splat_backward64(idx, height.numpy(), ctx.numpy(), gb.numpy(), *shape.grid)
+    np.testing.assert_allclose(g_hp.cpu().numpy(), gh64, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(g_cp.cpu().numpy(), gc64, rtol=1e-5, atol=1e-5)
+
+
+def test_channels_last_call_site_feeds_a_channels_last_trunk():
+    """LiftSplat(bev_channels_last=True) in front of a channels_last convolution: same loss and same gradients as
+    the contiguous module in front of the same convolution; unsupported combinations are refused."""
+    from sgv3d_b200 import LiftSplat
+    from sgv3d_b200 import view_transform as VT
+    from sgv3d_b200.synthetic import make_activations
+    shape = get_shape("small")
+    C = 32
+    mk = lambda **kw: LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
+                                shape.downsample, C, **kw).cuda()
+    mod, mod_cl = mk(), mk(bev_channels_last=True)
+    mats = make_mats(shape, 2, 1, seed=99, bda="random")
+    md = {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).cuda(), "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).cuda(),
+          "intrin_mats": mats["intrin"].unsqueeze(1).cuda(), "ida_mats": mats["ida"].unsqueeze(1).cuda(),
+          "reference_heights": mats["reference_heights"].unsqueeze(1).cuda(), "bda_mat": mats["bda"].cuda()}
+    logits, ctx = make_activations(shape, 2, 1, seed=99, channels=C)
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(C, 8, 3, padding=1).cuda()
+    conv_cl = torch.nn.Conv2d(C, 8, 3, padding=1).cuda()
+    conv_cl.load_state_dict(conv.state_dict())
+    conv_cl = conv_cl.to(memory_format=torch.channels_last)
+    outs = []
+    for m_, cv in ((mod, conv), (mod_cl, conv_cl)):
+        hf = torch.cat((logits, ctx), 1).cuda().requires_grad_(True)
+        bev = m_.forward_single_sweep(hf, md)
+        loss = cv(bev).square().mean()
+        loss.backward()
+        outs.append((bev.detach(), loss.detach(), hf.grad))
+    assert outs[1][0].is_contiguous(memory_format=torch.channels_last) and torch.equal(outs[0][0], outs[1][0])
+    torch.testing.assert_close(outs[1][1], outs[0][1], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(outs[1][2], outs[0][2], rtol=1e-3, atol=1e-6)   # (cuDNN picks other conv algorithms per layout)
+    with torch.no_grad():   # inference at a small batch: AUTO stays on the voxel-tile kernels for this layout
+        assert torch.equal(mod_cl.forward_single_sweep(torch.cat((logits, ctx), 1).cuda(), md), outs[0][0])
+    with pytest.raises(RuntimeError):
+        VT.LiftSplatPlan(mod.frustum, md["sensor2ego_mats"][:, 0], md["sensor2virtual_mats"][:, 0], md["intrin_mats"][:, 0],
+                         md["ida_mats"][:, 0], md["reference_heights"][:, 0], md["bda_mat"], mod.voxel_coord, mod.voxel_size,
+                         shape.grid, 7, channels_last=True)
+    with pytest.raises(RuntimeError):   # the 87-channel BSM map stays contiguous
+        patch_view_transform(BSMLSSFPNStandIn(shape, is_train_height=True).cuda(), bev_channels_last=True)
