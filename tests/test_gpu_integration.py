@@ -316,6 +316,31 @@ def test_channels_last_bev_map_and_gradient(channels):
     np.testing.assert_allclose(g_cp.cpu().numpy(), gc64, rtol=1e-5, atol=1e-5)
 
 
+def test_channels_last_with_bf16_context_and_an_empty_batch():
+    from oracle import lift_splat_oracle as O
+    from sgv3d_b200 import view_transform as VT
+    from sgv3d_b200.synthetic import make_activations
+    from tests.helpers import oracle_frustum
+    shape = get_shape("small")
+    fr = oracle_frustum(shape)
+    vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
+    for B in (2, 0):
+        mats = make_mats(shape, max(B, 1), 1, seed=81, bda="identity")
+        dev = {k: v.cuda()[:B] for k, v in mats.items()}
+        args = (fr, dev["sensor2ego"], dev["sensor2virtual"], dev["intrin"], dev["ida"], dev["reference_heights"], dev["bda"],
+                vc, vs, shape.grid, 80)
+        kw = dict(arith=0, pipeline=VT.PIPELINE_TILE, ctx_dtype=torch.bfloat16)
+        plan, plan_cl = VT.LiftSplatPlan(*args, **kw), VT.LiftSplatPlan(*args, channels_last=True, **kw)
+        logits, ctx = make_activations(shape, max(B, 1), 1, seed=5, channels=80)
+        lg, cg = logits.cuda()[:B], ctx.cuda()[:B].bfloat16()
+        bev, bev_cl = plan.forward(lg, cg, logits=True), plan_cl.forward(lg, cg, logits=True)
+        assert bev_cl.shape == (B, 80, shape.grid[1], shape.grid[0]) and torch.equal(bev_cl, bev)
+        gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(1)).cuda()
+        (g_h, g_c), (g_h2, g_c2) = plan.backward(gb, lg, cg, logits=True), plan_cl.backward(gb, lg, cg, logits=True)
+        assert torch.equal(g_c2, g_c)
+        torch.testing.assert_close(g_h2, g_h, rtol=1e-4, atol=1e-5)
+
+
 def test_channels_last_call_site_feeds_a_channels_last_trunk():
     """LiftSplat(bev_channels_last=True) in front of a channels_last convolution: same loss and same gradients as
     the contiguous module in front of the same convolution; unsupported combinations are refused."""
