@@ -43,7 +43,7 @@ RTOL_BF16, ATOL_BF16 = 1e-2, 1e-3  # bf16-context variant vs the fp32 oracle fed
 
 def _setup(shape_name, batch, num_cams, seed, bda, arith=0, ctx_dtype=torch.float32, peaky=False):
     from sgv3d_b200.view_transform import LiftSplatPlan
-    shape = get_shape(shape_name)
+    shape = get_shape(shape_name) if isinstance(shape_name, str) else shape_name
     mats = make_mats(shape, batch, num_cams, seed=seed, bda=bda)
     fr = oracle_frustum(shape)
     vs, vc, vn = O.grid_buffers(shape.x_bound, shape.y_bound, shape.z_bound)
@@ -587,3 +587,39 @@ def test_bsm_gradients_vs_oracle():
     torch.testing.assert_close(a[2].grad.cpu().double(), o[2].grad, rtol=RTOL, atol=ATOL)
     torch.testing.assert_close(a[1].grad.cpu().double(), o[1].grad, rtol=1e-4, atol=ATOL)
     torch.testing.assert_close(a[0].grad.cpu().double(), o[0].grad, rtol=1e-4, atol=ATOL)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_configurations_match_the_oracle(seed):
+    """Seeded random problem shapes -- image size, stride, number and range of the height bins, channels, grid extent and
+    cell size, z range, cameras per frame, BDA none / identity / random, all three arithmetic orders -- through plan ->
+    expand (bit-exact voxel ids), forward and backward (fp64 oracle), on whichever pipeline the fixture selects."""
+    from sgv3d_b200.shapes import LiftSplatShape
+    rng = np.random.default_rng(1000 + seed)
+    stride = int(rng.choice([8, 16]))
+    fh, fw = int(rng.integers(2, 12)), int(rng.integers(3, 20))
+    cell = float(rng.choice([0.8, 1.6, 3.2]))
+    nx, ny = int(rng.integers(6, 70)), int(rng.integers(6, 70))
+    z_lo = float(rng.choice([-5.0, -3.0, -1.0]))
+    z_hi = float(rng.choice([0.5, 3.0]))
+    d_lo = float(rng.choice([-2.0, -1.0, 0.0]))
+    shape = LiftSplatShape(f"random{seed}", (fh * stride + int(rng.integers(0, stride)), fw * stride + int(rng.integers(0, stride))),
+                           stride, (d_lo, d_lo + float(rng.choice([1.0, 2.0, 5.5])), int(rng.integers(1, 48))),
+                           int(rng.integers(1, 41)), x_bound=(0.0, nx * cell, cell), y_bound=(-ny * cell / 2, ny * cell / 2, cell),
+                           z_bound=(z_lo, z_hi, z_hi - z_lo), family=str(rng.choice(["dair", "rope3d"])), source="test-only")
+    batch, cams = int(rng.integers(1, 4)), int(rng.integers(1, 3))
+    bda = [None, "identity", "random"][int(rng.integers(0, 3))]
+    arith = int(rng.integers(0, 3))
+    shape, plan, idx, height, ctx = _setup(shape, batch, cams, 500 + seed, bda, arith=arith, peaky=bool(seed % 2))
+    X, Y, Z = shape.grid
+    kept = kept_mask_np(idx, shape.grid)
+    want_vox = np.where(kept, idx[..., 1] * X + idx[..., 0], -1).astype(np.int32)
+    assert int((plan.expand().cpu().numpy() != want_vox).sum()) == 0, (shape, batch, cams, bda, arith)
+    bev = plan.forward(height.cuda(), ctx.cuda())
+    want = CO.lift_splat_forward64(idx, height.numpy(), ctx.numpy(), X, Y, Z)
+    np.testing.assert_allclose(bev.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    gb = torch.randn(bev.shape, generator=torch.Generator().manual_seed(seed))
+    g_h, g_c = plan.backward(gb.cuda(), height.cuda(), ctx.cuda())
+    gh64, gc64 = CO.lift_splat_backward64(idx, height.numpy(), ctx.numpy(), gb.numpy(), X, Y, Z)
+    np.testing.assert_allclose(g_h.cpu().numpy(), gh64, rtol=RTOL, atol=ATOL * 10)
+    np.testing.assert_allclose(g_c.cpu().numpy(), gc64, rtol=RTOL, atol=ATOL)
