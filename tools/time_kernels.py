@@ -9,6 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="dair_r50"); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--iters", type=int, default=20); ap.add_argument("--bf16", action="store_true")
 ap.add_argument("--pipeline", default="auto", choices=["auto", "tile", "block"])
+ap.add_argument("--bda", default="identity", choices=["identity", "random", "none"])
 ap.add_argument("--channels-last", action="store_true", help="BEV map / gradient in torch.channels_last order")
 a = ap.parse_args()
 from sgv3d_b200 import view_transform as VT  # noqa: E402
@@ -16,10 +17,11 @@ VT.set_default_pipeline({"auto": VT.PIPELINE_AUTO, "tile": VT.PIPELINE_TILE, "bl
 s = get_shape(a.shape); dev = torch.device("cuda", 0)
 mod = LiftSplat(s.x_bound, s.y_bound, s.z_bound, s.d_bound, s.final_dim, s.downsample, s.channels,
                 bev_channels_last=a.channels_last).to(dev)
-mats = make_mats(s, a.batch, 1, seed=5, bda="identity")
+mats = make_mats(s, a.batch, 1, seed=5, bda=None if a.bda == "none" else a.bda)
 md = {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).to(dev), "sensor2virtual_mats": mats["sensor2virtual"].unsqueeze(1).to(dev),
       "intrin_mats": mats["intrin"].unsqueeze(1).to(dev), "ida_mats": mats["ida"].unsqueeze(1).to(dev),
-      "reference_heights": mats["reference_heights"].unsqueeze(1).to(dev), "bda_mat": mats["bda"].to(dev)}
+      "reference_heights": mats["reference_heights"].unsqueeze(1).to(dev),
+      "bda_mat": mats["bda"].to(dev) if mats["bda"] is not None else None}
 logits, ctx = make_activations(s, a.batch, 1, seed=5, device=dev, generator_device=dev)
 if a.bf16:
     ctx = ctx.bfloat16()
