@@ -729,13 +729,25 @@ __device__ __forceinline__ float column_exp_sum(float *col, int lo, int hi, int 
   return __fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3]));
 }
 
+// BSMLSSFPN context assembly (bsm_lss_fpn.py:524-529), fused into the context-rows pass when `sem` is set:
+//   semantic = softmax(sem, channel axis);  rows = cat(context, semantic) * (1 - (semantic[0] > thr))
+// The last Cs of the C row channels are the semantic probabilities; `context` holds the other C - Cs.
+struct BsmAssembly {
+  const float *sem;      // [B*Nc, Cs, fH, fW] semantic logits, or nullptr
+  long long sem_stride;  // elements between consecutive cameras
+  int Cs;
+  float thr;
+};
+
+
 // vm_ent_out != nullptr: forward, the weight goes to the run's voxel-major entry (through run_dst);
 // else backward (unfused path), pixel-major w_pm_out.  256 threads: thread (t, h) owns half h of pixel t's
 // column for the softmax statistics and the runs r = h mod 2.
 __device__ __forceinline__ void weights_role(const Dims &m, const float *__restrict__ height, int vec16,
                                              const int *__restrict__ run_cnt, const int *__restrict__ run_d,
                                              const int *__restrict__ run_dst, float *__restrict__ w_pm_out,
-                                             Entry *__restrict__ vm_ent_out, float *col, int b, int chunk) {
+                                             Entry *__restrict__ vm_ent_out, float *col, int b, int chunk,
+                                             const BsmAssembly &bsm) {
   __shared__ float s_max[2][kChunk], s_sum[2][kChunk];
   const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
   const int frame_chunk = b * m.nchunks + chunk;
@@ -744,6 +756,18 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   stage_columns(col, height + (size_t)(b * m.Nc + n) * m.hs, m.D, m.P, p0, vec16 != 0);
   const bool live = p0 + t < m.P;
   const int cnt = live ? run_cnt[(size_t)frame_chunk * kChunk + t] : 0;
+  // BSMLSSFPN: a background pixel (semantic[0] > thr, bsm_lss_fpn.py:528-529) has an all-zero context row.  Its runs
+  // get the weight -0.0f: the reduce recognises the bit pattern and does not gather the row (w * 0 = 0 either way;
+  // real roadside frames are mostly background).  Same arithmetic as the context-rows role.
+  bool masked = false;
+  if (bsm.sem && live && vm_ent_out) {
+    const float *ss = bsm.sem + (size_t)(b * m.Nc + n) * bsm.sem_stride + p0 + t;
+    float mx = ss[0];
+    for (int k = 1; k < bsm.Cs; ++k) mx = fmaxf(mx, ss[(size_t)k * m.P]);
+    float sum = 0.0f;
+    for (int k = 0; k < bsm.Cs; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(ss[(size_t)k * m.P], mx)));
+    masked = __fdiv_rn(expf(__fsub_rn(ss[0], mx)), sum) > bsm.thr;
+  }
   // the first run descriptors are requested before the softmax so that their latency hides behind it
   constexpr int kPre = 6;
   int pre_d[kPre], pre_dst[kPre];
@@ -771,8 +795,9 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   auto emit = [&](int r, int packed, int dst) {
     const int d0 = packed & 0xffff, d1 = packed >> 16;
     float acc = 0.0f;
-    for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-    const float wgt = m.logits ? __fmul_rn(acc, scale) : acc;
+    if (!masked)
+      for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
+    const float wgt = masked ? -0.0f : (m.logits ? __fmul_rn(acc, scale) : acc);
     if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + dst].w = wgt;
     else w_pm_out[ell_slot(frame_chunk, m.D, r, t)] = wgt;
   };
@@ -801,16 +826,6 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
 // order, transpose.cuh: RowPerm).  Reads are coalesced 512-byte channel rows (cp.async, all in flight at
 // once), writes are coalesced 128-byte pieces of the pixel rows; the smem tile is [C][129] (conflict-free
 // both ways: consecutive pixels on the way in, 32 distinct channels of one pixel on the way out).
-// BSMLSSFPN context assembly (bsm_lss_fpn.py:524-529), fused into the context-rows pass when `sem` is set:
-//   semantic = softmax(sem, channel axis);  rows = cat(context, semantic) * (1 - (semantic[0] > thr))
-// The last Cs of the C row channels are the semantic probabilities; `context` holds the other C - Cs.
-struct BsmAssembly {
-  const float *sem;      // [B*Nc, Cs, fH, fW] semantic logits, or nullptr
-  long long sem_stride;  // elements between consecutive cameras
-  int Cs;
-  float thr;
-};
-
 template <typename CT>
 __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__restrict__ context,
                                                   CT *__restrict__ ctxT, RowPerm perm, float *smem, int b,
@@ -890,7 +905,7 @@ ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const i
                     const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm, BsmAssembly bsm) {
   extern __shared__ __align__(128) float lift_smem[];
   if (blockIdx.z == 0)
-    weights_role(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x);
+    weights_role(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x, bsm);
   else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x, bsm);
 }
 
@@ -1033,13 +1048,21 @@ __device__ __forceinline__ void flush_voxel(StreamAcc<G, NV> &acc, unsigned tile
   }
 }
 
-template <typename CT, int G, int NV, bool STAGED, bool CL>
+// SKIP: entries whose weight is -0.0f (background pixels of the BSM call site: weights_role) do not gather their row.
+template <typename CT, int G, int NV, bool STAGED, bool CL, bool SKIP>
 __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, bool &head,
                                             const Entry *__restrict__ ent, int tile_lo, int j0, int j1,
                                             const unsigned char *__restrict__ lane_rows, unsigned tile_lane,
                                             float *my_head, int l, unsigned box_bytes, const ClOut &cl) {
   constexpr unsigned kRowBytes = 4 * G * NV * sizeof(CT);
   auto load_row = [&](const Entry &en, float (&r)[NV][4]) {
+    if (SKIP && __float_as_uint(en.w) == 0x80000000u) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[k][e] = 0.0f;
+      return;
+    }
     const unsigned char *row = lane_rows + (size_t)(en.off >> 6) * kRowBytes;
 #pragma unroll
     for (int k = 0; k < NV; ++k) RowLd<CT>::vec(row + k * G * 4 * sizeof(CT), r[k]);
@@ -1099,7 +1122,7 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
 //   CL (channels-last BEV map, desc.reserved[1] bit 1): the tile is [voxel][C] rows instead, a finished voxel's sums
 //      are one row of it, and the tile -- 64 adjacent rows of the (b, y, x, c) map, one contiguous block of memory --
 //      leaves with a single bulk-async (TMA) shared -> global copy.
-template <typename CT, int G, int NV, int NSTR, bool CL>
+template <typename CT, int G, int NV, int NSTR, bool CL, bool SKIP>
 __global__ void __launch_bounds__(NSTR * G)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ tile_ptr,
                  const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out, int stage_cap) {
@@ -1169,9 +1192,9 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
   bool head = false;    // the segment being accumulated continues a voxel started by an earlier stream
   const Entry *se = s_ent - tile_lo;  // staged entries, addressed like the plan's
   if (staged)
-    stream_loop<CT, G, NV, true, CL>(acc, cur, head, se, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes, cl);
+    stream_loop<CT, G, NV, true, CL, SKIP>(acc, cur, head, se, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes, cl);
   else
-    stream_loop<CT, G, NV, false, CL>(acc, cur, head, ent, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes, cl);
+    stream_loop<CT, G, NV, false, CL, SKIP>(acc, cur, head, ent, tile_lo, j0, j1, lane_rows, tile_lane, my_head, l, kBoxBytes, cl);
   // voxel (in tile) of entry j
   auto vox_at = [&](int j) -> int {
     return (int)((staged ? load_entry<true>(se, j) : load_entry<false>(ent, j)).off & 63u);
@@ -1734,7 +1757,7 @@ int check_ws(const Workspace &w, void *ws, size_t bytes, const char *who) {
 }
 
 template <typename CT, int G, int NV, int NSTR>
-int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s, bool skip) {
   dim3 grid(ceil_div(m.V, kTileV), m.B);
   // expected entries per touched tile ~ pixels * (runs per pixel ~ 25) / (touched tiles ~ 170 per 128 x 128
   // grid); stage up to ~2x that, within 1.5 K .. 6 K entries (12 .. 48 KB)
@@ -1746,12 +1769,16 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
   if (m.cl) {
     SGV3D_REQUIRE(reinterpret_cast<uintptr_t>(bev) % 16 == 0, "lift_splat_forward: channels-last BEV map must be 16-byte aligned");
-    if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, true>, smem)) return rc;
-    ls_reduce_kernel<CT, G, NV, NSTR, true><<<grid, NSTR * G, smem, s>>>(
+    if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, true, false>, smem)) return rc;
+    ls_reduce_kernel<CT, G, NV, NSTR, true, false><<<grid, NSTR * G, smem, s>>>(
         m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+  } else if (skip && sizeof(CT) == 4) {   // BSM call site (fp32 context): background pixels carry the weight -0.0f
+    if (int rc = set_smem(ls_reduce_kernel<float, G, NV, NSTR, false, true>, smem)) return rc;
+    ls_reduce_kernel<float, G, NV, NSTR, false, true><<<grid, NSTR * G, smem, s>>>(
+        m, static_cast<const float *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
   } else {
-    if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, false>, smem)) return rc;
-    ls_reduce_kernel<CT, G, NV, NSTR, false><<<grid, NSTR * G, smem, s>>>(
+    if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, false, false>, smem)) return rc;
+    ls_reduce_kernel<CT, G, NV, NSTR, false, false><<<grid, NSTR * G, smem, s>>>(
         m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
   }
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
@@ -1759,30 +1786,30 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
 }
 
 template <typename CT, int G, int NV>
-int launch_reduce_nstr(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+int launch_reduce_nstr(const Dims &m, const Workspace &w, float *bev, cudaStream_t s, bool skip) {
   // streams per tile by the expected tile population (pixels * ~25 runs / ~2/3 of the tiles touched): a tile is
   // one CTA, so the most populated tiles of a dense feature map (stride 8) set the kernel's tail
   const long long expect = (long long)m.Nc * m.P * 25 / (m.ntiles * 2 / 3 + 1);
   // (small batches are bound by the tail: twice the streams again; measured on DAIR-R50 and BSM-R50)
   const int nstr = expect > 6000 ? 128 : (expect > 1500 ? (m.B <= 8 ? 128 : 64) : (m.B <= 2 ? 64 : 32));
-  if (nstr == 128) return launch_reduce_cfg<CT, G, NV, 128>(m, w, bev, s);
-  if (nstr == 64) return launch_reduce_cfg<CT, G, NV, 64>(m, w, bev, s);
-  return launch_reduce_cfg<CT, G, NV, 32>(m, w, bev, s);
+  if (nstr == 128) return launch_reduce_cfg<CT, G, NV, 128>(m, w, bev, s, skip);
+  if (nstr == 64) return launch_reduce_cfg<CT, G, NV, 64>(m, w, bev, s, skip);
+  return launch_reduce_cfg<CT, G, NV, 32>(m, w, bev, s, skip);
 }
 
 template <typename CT>
-int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s) {
+int launch_reduce(const Dims &m, const Workspace &w, float *bev, cudaStream_t s, bool skip = false) {
   if (m.G == 8) {
     switch (m.NV) {
-      case 1: return launch_reduce_nstr<CT, 8, 1>(m, w, bev, s);
-      case 2: return launch_reduce_nstr<CT, 8, 2>(m, w, bev, s);
-      case 3: return launch_reduce_nstr<CT, 8, 3>(m, w, bev, s);
-      case 4: return launch_reduce_nstr<CT, 8, 4>(m, w, bev, s);
-      case 5: return launch_reduce_nstr<CT, 8, 5>(m, w, bev, s);
-      default: return launch_reduce_nstr<CT, 8, 6>(m, w, bev, s);
+      case 1: return launch_reduce_nstr<CT, 8, 1>(m, w, bev, s, skip);
+      case 2: return launch_reduce_nstr<CT, 8, 2>(m, w, bev, s, skip);
+      case 3: return launch_reduce_nstr<CT, 8, 3>(m, w, bev, s, skip);
+      case 4: return launch_reduce_nstr<CT, 8, 4>(m, w, bev, s, skip);
+      case 5: return launch_reduce_nstr<CT, 8, 5>(m, w, bev, s, skip);
+      default: return launch_reduce_nstr<CT, 8, 6>(m, w, bev, s, skip);
     }
   }
-  return launch_reduce_cfg<CT, 16, 4, 16>(m, w, bev, s);
+  return launch_reduce_cfg<CT, 16, 4, 16>(m, w, bev, s, skip);
 }
 
 template <typename CT, int NV>
@@ -2056,7 +2083,7 @@ extern "C" int sgv3d_lift_splat_forward_bsm(const sgv3d_lift_splat_desc *desc, c
   bsm.Cs = semantic_channels;
   bsm.thr = background_threshold;
   if (int rc = launch_lift_prep(m, w, desc->ctx_dtype, height, context, true, s, bsm)) return rc;
-  return launch_reduce<float>(m, w, bev, s);
+  return launch_reduce<float>(m, w, bev, s, /*skip background pixels' rows*/ true);
 }
 
 extern "C" int sgv3d_lift_splat_backward(const sgv3d_lift_splat_desc *desc, const float *grad_bev,

@@ -7,7 +7,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sgv3d_b200 import LiftSplat, get_shape  # noqa: E402
 from sgv3d_b200.synthetic import make_mats  # noqa: E402
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=8); ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--background", type=float, default=-1.0, help="fraction of background pixels (semantic[0] > 0.45); default: random logits")
+ap.add_argument("--pipeline", default="auto", choices=["auto", "tile", "block"])
 a = ap.parse_args()
+from sgv3d_b200 import view_transform as VT  # noqa: E402
+VT.set_default_pipeline({"auto": VT.PIPELINE_AUTO, "tile": VT.PIPELINE_TILE, "block": VT.PIPELINE_BLOCK}[a.pipeline])
 s = get_shape("sgv3d_bsm_r50"); dev = torch.device("cuda", 0); B = a.batch
 mod = LiftSplat(s.x_bound, s.y_bound, s.z_bound, s.d_bound, s.final_dim, s.downsample, 87).to(dev)
 mats = make_mats(s, B, 1, seed=5, bda="identity")
@@ -15,6 +19,10 @@ md = {"sensor2ego_mats": mats["sensor2ego"].unsqueeze(1).to(dev), "sensor2virtua
       "intrin_mats": mats["intrin"].unsqueeze(1).to(dev), "ida_mats": mats["ida"].unsqueeze(1).to(dev),
       "reference_heights": mats["reference_heights"].unsqueeze(1).to(dev), "bda_mat": mats["bda"].to(dev)}
 hl = torch.randn(B, s.D, s.fH, s.fW, device=dev); sl = torch.randn(B, 7, s.fH, s.fW, device=dev); cx = torch.randn(B, 80, s.fH, s.fW, device=dev)
+if a.background >= 0:   # real roadside frames are mostly background: push channel 0 up on that fraction of the pixels
+    bg = torch.rand(B, s.fH, s.fW, device=dev) < a.background
+    sl[:, 0] = torch.where(bg, torch.full_like(sl[:, 0], 6.0), torch.full_like(sl[:, 0], -6.0))
+print("background fraction", float((sl.softmax(1)[:, 0] > 0.45).float().mean()), "pipeline", a.pipeline, flush=True)
 
 def fused():
     with torch.no_grad():
