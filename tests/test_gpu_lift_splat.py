@@ -342,8 +342,9 @@ def test_static_calibration_graph_and_refresh():
         g(hf, md_b)     # a different mats_dict must go through refresh_calibration()
 
 
-@pytest.mark.parametrize("shape_name,batch", [("small", 2), ("sgv3d_bsm_r50", 1)])
-def test_fused_bsm_assembly_is_bit_identical_to_the_torch_assembly(shape_name, batch):
+@pytest.mark.parametrize("shape_name,batch,bg_shift", [("small", 2, 1.6), ("sgv3d_bsm_r50", 1, 1.6), ("small", 2, 5.0),
+                                                       ("sgv3d_bsm_r50", 1, 5.0), ("small", 2, -4.0), ("small", 2, 50.0)])
+def test_fused_bsm_assembly_is_bit_identical_to_the_torch_assembly(shape_name, batch, bg_shift):
     """sgv3d_lift_splat_forward_bsm (softmax over the semantic channels + concat + background mask inside the
     context pass, bsm_lss_fpn.py:524-529) == the same torch calls the reference makes, run on the GPU, followed by
     the plain forward: the background mask must be bit-identical, hence the BEV map bitwise equal."""
@@ -356,7 +357,7 @@ def test_fused_bsm_assembly_is_bit_identical_to_the_torch_assembly(shape_name, b
     height_logits = torch.randn(batch, shape.D, fh, fw, generator=g).cuda()
     # logits scaled so that the background probability straddles the 0.45 threshold for many pixels
     semantic_logits = (torch.randn(batch, 7, fh, fw, generator=g) * 1.5).cuda()
-    semantic_logits[:, 0] += 1.6
+    semantic_logits[:, 0] += bg_shift   # 1.6: about half of the pixels are background; 5: ~90 % (a roadside frame); 50: all
     context = torch.randn(batch, 80, fh, fw, generator=g).cuda()
     mod = LiftSplat(shape.x_bound, shape.y_bound, shape.z_bound, shape.d_bound, shape.final_dim,
                     shape.downsample * (1 if bsm_native else 1), 87, is_bsm=not bsm_native).cuda()
@@ -373,7 +374,8 @@ def test_fused_bsm_assembly_is_bit_identical_to_the_torch_assembly(shape_name, b
     tran_feat = torch.cat((context, semantic), dim=1)
     mask = semantic[:, 0, :, :].unsqueeze(1) > 0.45
     frac = float(mask.float().mean())
-    assert 0.2 < frac < 0.8, frac          # the threshold is exercised on both sides
+    lo, hi = {1.6: (0.2, 0.8), 5.0: (0.8, 0.99), -4.0: (0.0, 0.05), 50.0: (1.0, 1.0)}[bg_shift]
+    assert lo <= frac <= hi, frac          # (1.6: the threshold is exercised on both sides)
     tran_feat = tran_feat * (1 - mask.int())
     plan = mod.make_plan(md, 0, 87)
     want = plan.forward(height_logits, tran_feat.float(), logits=True)

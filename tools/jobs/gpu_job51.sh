@@ -1,0 +1,3 @@
+(timeout 1200 python -m pytest tests/test_gpu_lift_splat.py tests/test_gpu_integration.py -q -x --tb=short -p no:cacheprovider --timeout 900 -k "bsm or BSM" 2>&1 | tail -8)
+for bg in -1 0.5 0.9; do timeout 200 python tools/time_bsm.py --batch 16 --background $bg --pipeline tile 2>&1 | tail -1; done
+timeout 120 python tools/time_kernels.py --shape dair_r50 --batch 64 --pipeline tile --iters 30 2>&1 | sed -n 2p

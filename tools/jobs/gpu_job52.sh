@@ -1,0 +1,1 @@
+(timeout 1200 python -m pytest tests/test_gpu_lift_splat.py tests/test_gpu_integration.py -q -x --tb=short -p no:cacheprovider --timeout 900 -k "bsm or BSM" 2>&1 | tail -4)
