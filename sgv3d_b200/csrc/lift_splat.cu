@@ -785,10 +785,11 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   if (m.logits) {  // block-uniform
     const int half = (m.D + 1) >> 1;
     const int lo = h * half, hi = min(m.D, lo + half);
-    s_max[h][t] = (live && cnt > 0) ? column_max(col, lo, hi, t) : 0.0f;
+    const bool work = live && cnt > 0 && !masked;   // (a background pixel's weights are -0.0f whatever its heights)
+    s_max[h][t] = work ? column_max(col, lo, hi, t) : 0.0f;
     __syncthreads();
     const float mx = fmaxf(s_max[0][t], s_max[1][t]);
-    s_sum[h][t] = (live && cnt > 0) ? column_exp_sum(col, lo, hi, t, mx) : 1.0f;
+    s_sum[h][t] = work ? column_exp_sum(col, lo, hi, t, mx) : 1.0f;
     __syncthreads();  // both halves of every column now hold exp(x - max)
     scale = __fdiv_rn(1.0f, __fadd_rn(s_sum[0][t], s_sum[1][t]));
   }
