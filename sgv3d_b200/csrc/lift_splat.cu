@@ -743,6 +743,7 @@ struct BsmAssembly {
 // vm_ent_out != nullptr: forward, the weight goes to the run's voxel-major entry (through run_dst);
 // else backward (unfused path), pixel-major w_pm_out.  256 threads: thread (t, h) owns half h of pixel t's
 // column for the softmax statistics and the runs r = h mod 2.
+template <bool BSM>
 __device__ __forceinline__ void weights_role(const Dims &m, const float *__restrict__ height, int vec16,
                                              const int *__restrict__ run_cnt, const int *__restrict__ run_d,
                                              const int *__restrict__ run_dst, float *__restrict__ w_pm_out,
@@ -760,7 +761,7 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   // get the weight -0.0f: the reduce recognises the bit pattern and does not gather the row (w * 0 = 0 either way;
   // real roadside frames are mostly background).  Same arithmetic as the context-rows role.
   bool masked = false;
-  if (bsm.sem && live && vm_ent_out) {
+  if (BSM && bsm.sem && live && vm_ent_out) {
     const float *ss = bsm.sem + (size_t)(b * m.Nc + n) * bsm.sem_stride + p0 + t;
     float mx = ss[0];
     for (int k = 1; k < bsm.Cs; ++k) mx = fmaxf(mx, ss[(size_t)k * m.P]);
@@ -785,7 +786,7 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   if (m.logits) {  // block-uniform
     const int half = (m.D + 1) >> 1;
     const int lo = h * half, hi = min(m.D, lo + half);
-    const bool work = live && cnt > 0 && !masked;   // (a background pixel's weights are -0.0f whatever its heights)
+    const bool work = live && cnt > 0 && !(BSM && masked);   // (a background pixel's weights are -0.0f whatever its heights)
     s_max[h][t] = work ? column_max(col, lo, hi, t) : 0.0f;
     __syncthreads();
     const float mx = fmaxf(s_max[0][t], s_max[1][t]);
@@ -796,9 +797,9 @@ __device__ __forceinline__ void weights_role(const Dims &m, const float *__restr
   auto emit = [&](int r, int packed, int dst) {
     const int d0 = packed & 0xffff, d1 = packed >> 16;
     float acc = 0.0f;
-    if (!masked)
+    if (!(BSM && masked))
       for (int d = d0; d < d1; ++d) acc = __fadd_rn(acc, col[d * kChunk + t]);
-    const float wgt = masked ? -0.0f : (m.logits ? __fmul_rn(acc, scale) : acc);
+    const float wgt = (BSM && masked) ? -0.0f : (m.logits ? __fmul_rn(acc, scale) : acc);
     if (vm_ent_out) vm_ent_out[(size_t)b * m.cap + dst].w = wgt;
     else w_pm_out[ell_slot(frame_chunk, m.D, r, t)] = wgt;
   };
@@ -898,7 +899,7 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
 
 // One launch, two kinds of CTA (blockIdx.z): run weights of a pixel chunk (ALU / latency bound) and
 // channels-last context rows of a pixel chunk (bandwidth bound) -- they overlap on every SM.
-template <typename CT>
+template <typename CT, bool BSM>
 __global__ void __launch_bounds__(kPrepThreads)
 ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
                     const int *__restrict__ run_d, const int *__restrict__ run_dst,
@@ -906,7 +907,7 @@ ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const i
                     const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm, BsmAssembly bsm) {
   extern __shared__ __align__(128) float lift_smem[];
   if (blockIdx.z == 0)
-    weights_role(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x, bsm);
+    weights_role<BSM>(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x, bsm);
   else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x, bsm);
 }
 
@@ -1891,15 +1892,22 @@ int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const flo
   const size_t smem2 = sizeof(float) * (size_t)kChunk * m.D > smem ? sizeof(float) * (size_t)kChunk * m.D : smem;
   const int vec16 = columns_vec16(height, m.hs, m.P) ? 1 : 0;
   if (ctx_dtype == SGV3D_DTYPE_BF16) {
-    if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16>, smem2)) return rc;
-    ls_lift_prep_kernel<__nv_bfloat16><<<grid, kPrepThreads, smem2, s>>>(
+    if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16, false>, smem2)) return rc;
+    ls_lift_prep_kernel<__nv_bfloat16, false><<<grid, kPrepThreads, smem2, s>>>(
         m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm, vm_out, static_cast<const __nv_bfloat16 *>(context),
         static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m), bsm);
   } else {
-    if (int rc = set_smem(ls_lift_prep_kernel<float>, smem2)) return rc;
-    ls_lift_prep_kernel<float><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
-                                                          vm_out, static_cast<const float *>(context),
-                                                          static_cast<float *>(w.ctxT), row_perm(m), bsm);
+    if (bsm.sem) {
+      if (int rc = set_smem(ls_lift_prep_kernel<float, true>, smem2)) return rc;
+      ls_lift_prep_kernel<float, true><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
+                                                                  vm_out, static_cast<const float *>(context),
+                                                                  static_cast<float *>(w.ctxT), row_perm(m), bsm);
+    } else {
+      if (int rc = set_smem(ls_lift_prep_kernel<float, false>, smem2)) return rc;
+      ls_lift_prep_kernel<float, false><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
+                                                                   vm_out, static_cast<const float *>(context),
+                                                                   static_cast<float *>(w.ctxT), row_perm(m), bsm);
+    }
   }
   SGV3D_CHECK_LAUNCH("ls_lift_prep_kernel");
   return SGV3D_OK;
