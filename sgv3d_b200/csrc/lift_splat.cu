@@ -31,6 +31,7 @@
 //     (C > 96: ls_lift_prep_kernel, transpose_pad_kernel, ls_backward_gather_kernel, ls_expand_kernel)
 //
 // No floating-point atomics anywhere; every sum has a fixed order => bitwise reproducible.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
@@ -1127,7 +1128,8 @@ __device__ __forceinline__ void stream_loop(StreamAcc<G, NV> &acc, int &cur, boo
 template <typename CT, int G, int NV, int NSTR, bool CL, bool SKIP>
 __global__ void __launch_bounds__(NSTR * G)
 ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ tile_ptr,
-                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out, int stage_cap) {
+                 const Entry *__restrict__ vm_ent, float *__restrict__ bev, int vec_out, int stage_cap,
+                 const __grid_constant__ CUtensorMap bev_map) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int kThreads = NSTR * G;
   constexpr int kRows = 4 * G * NV;                  // = Cpad rows (rows >= C are scratch)
@@ -1233,7 +1235,27 @@ ls_reduce_kernel(Dims m, const CT *__restrict__ ctxT, const int *__restrict__ ti
     return;
   }
 
-  // tile -> global: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line.
+  // tile -> global.  vec_out == 2: the two 32-voxel boxes of the tile ARE TMA boxes (128-byte rows, SWIZZLE_128B):
+  // one thread hands each to the TMA engine as a 2-D tensor store ({32 voxels, C channel planes} at (v0, b * C) of
+  // the (B * C) x V view of the map) and the CTA retires once the engine has read shared memory -- no LDS / STG.
+  if (vec_out == 2) {
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const unsigned long long mp = reinterpret_cast<unsigned long long>(&bev_map);
+      const int y = b * m.C;
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(mp), "r"(v0), "r"(y),
+                   "r"(smem_u32(tile))
+                   : "memory");
+      if (nv > 32)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(mp), "r"(v0 + 32),
+                     "r"(y), "r"(smem_u32(tile) + kBoxBytes)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  // vec_out == 1: thread = (channel row, 16-byte chunk); 8 consecutive lanes write one 128-byte line.
   // Rows advance by a multiple of 8 per step, so (row & 7) and with it the swizzled chunk position never change.
   if (vec_out) {
     if (4 * q < nv) {
@@ -1758,6 +1780,31 @@ int check_ws(const Workspace &w, void *ws, size_t bytes, const char *who) {
   return SGV3D_OK;
 }
 
+// 2-D tensor map of the contiguous (B, C, Y, X) map viewed as (B * C) rows of V voxels, box = {32 voxels, C rows},
+// SWIZZLE_128B (the reduce tile's layout).  The driver entry point is looked up once; without it the reduce keeps
+// its LDS / STG copy-out.
+bool make_bev_map(const Dims &m, float *bev, CUtensorMap *map) {
+  typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static const Encode encode = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (getenv("SGV3D_NO_TMA_STORE")) return (Encode) nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<Encode>(fn);
+  }();
+  if (!encode || m.V % 4 != 0 || m.C > 256 || reinterpret_cast<uintptr_t>(bev) % 16 != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)m.V, (cuuint64_t)m.B * m.C};
+  const cuuint64_t strides[1] = {(cuuint64_t)m.V * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)m.C};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bev, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename CT, int G, int NV, int NSTR>
 int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_t s, bool skip) {
   dim3 grid(ceil_div(m.V, kTileV), m.B);
@@ -1768,20 +1815,23 @@ int launch_reduce_cfg(const Dims &m, const Workspace &w, float *bev, cudaStream_
   while (stage_cap < 2 * expect && stage_cap < 6144) stage_cap += 1536;
   const size_t smem = (size_t)2 * m.Cpad * 128 + sizeof(float) * NSTR * m.Cpad + sizeof(Entry) * stage_cap;
   // 128-bit output stores need 16-byte aligned voxel quads in every channel plane
-  const int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
+  int vec_out = (m.V % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0);
+  CUtensorMap bev_map;
+  memset(&bev_map, 0, sizeof(bev_map));
+  if (!m.cl && vec_out && make_bev_map(m, bev, &bev_map)) vec_out = 2;
   if (m.cl) {
     SGV3D_REQUIRE(reinterpret_cast<uintptr_t>(bev) % 16 == 0, "lift_splat_forward: channels-last BEV map must be 16-byte aligned");
     if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, true, false>, smem)) return rc;
     ls_reduce_kernel<CT, G, NV, NSTR, true, false><<<grid, NSTR * G, smem, s>>>(
-        m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+        m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap, bev_map);
   } else if (skip && sizeof(CT) == 4) {   // BSM call site (fp32 context): background pixels carry the weight -0.0f
     if (int rc = set_smem(ls_reduce_kernel<float, G, NV, NSTR, false, true>, smem)) return rc;
     ls_reduce_kernel<float, G, NV, NSTR, false, true><<<grid, NSTR * G, smem, s>>>(
-        m, static_cast<const float *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+        m, static_cast<const float *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap, bev_map);
   } else {
     if (int rc = set_smem(ls_reduce_kernel<CT, G, NV, NSTR, false, false>, smem)) return rc;
     ls_reduce_kernel<CT, G, NV, NSTR, false, false><<<grid, NSTR * G, smem, s>>>(
-        m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap);
+        m, static_cast<const CT *>(w.ctxT), w.tile_ptr, w.vm_ent, bev, vec_out, stage_cap, bev_map);
   }
   SGV3D_CHECK_LAUNCH("ls_reduce_kernel");
   return SGV3D_OK;
