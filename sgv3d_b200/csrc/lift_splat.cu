@@ -1408,6 +1408,48 @@ ls_grad_rows_kernel(Dims m, const float *__restrict__ grad_bev, const int *__res
   }
 }
 
+// The same with the TMA engine on the way in: the tile's two {32 voxels, C planes} boxes of the (B*C) x V view of grad_bev
+// arrive with two 2-D tensor loads (SWIZZLE_128B, completion on an mbarrier) instead of 4-byte cp.async copies; a thread
+// then moves 16-byte chunks (4 voxels of one channel: conflict-free per quarter warp) into 4 rows.
+__global__ void __launch_bounds__(256)
+ls_grad_rows_tma_kernel(Dims m, const int *__restrict__ tile_ptr, float *__restrict__ gT, RowPerm perm,
+                        const __grid_constant__ CUtensorMap g_map) {
+  extern __shared__ __align__(1024) unsigned char gbox[];   // 2 boxes x C rows x 128 B, each box on a 1 KB boundary
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int *tp = tile_ptr + (size_t)b * (m.ntiles + 1) + tile;
+  if (__ldg(tp) == __ldg(tp + 1)) return;
+  const int v0 = tile * kTileV;
+  const int nv = min(kTileV, m.V - v0);
+  // (the 128-byte swizzle works on shared-memory ADDRESS bits 7-9: a box must start on a 1 KB boundary for "row & 7" to be them)
+  const unsigned box_bytes = (((unsigned)m.C + 7u) >> 3) * 1024u;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_arrive_expect_tx(&s_bar, 2u * (unsigned)m.C * 128u);   // (out-of-range voxels of the last tile are zero-filled and counted)
+    const unsigned long long mp = reinterpret_cast<unsigned long long>(&g_map);
+    for (int k = 0; k < 2; ++k)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                       smem_u32(gbox) + k * box_bytes),
+                   "l"(mp), "r"(v0 + 32 * k), "r"(b * m.C), "r"(smem_u32(&s_bar))
+                   : "memory");
+  }
+  __syncthreads();   // the barrier is initialised before anybody waits on it
+  mbar_wait(&s_bar, 0);
+  float *dst = gT + ((size_t)b * m.V + v0) * m.Cpad;
+  for (int idx = threadIdx.x; idx < 16 * m.Cpad; idx += 256) {
+    const int jq = idx / m.Cpad, e = idx - jq * m.Cpad;   // voxel quad, element of the row
+    const int c = perm.chan(e);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < m.C)
+      v = *reinterpret_cast<const float4 *>(gbox + (jq >> 3) * box_bytes + c * 128 + (((jq & 7) ^ (c & 7)) << 4));
+    float *dp = dst + (size_t)(4 * jq) * m.Cpad + e;
+    if (4 * jq + 0 < nv) dp[0] = v.x;
+    if (4 * jq + 1 < nv) dp[m.Cpad] = v.y;
+    if (4 * jq + 2 < nv) dp[2 * m.Cpad] = v.z;
+    if (4 * jq + 3 < nv) dp[3 * m.Cpad] = v.w;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // BACKWARD, fused per pixel chunk (rows of <= 96 channels): one CTA = 64 pixels x 4 lanes.
 //   1. the chunk's D x 64 height block and C x 64 context block are staged with cp.async (coalesced,
@@ -1974,10 +2016,19 @@ int launch_backward_fused(const Dims &m, const Workspace &w, int ctx_dtype, cons
     SGV3D_REQUIRE(reinterpret_cast<uintptr_t>(grad_bev) % 16 == 0, "lift_splat_backward: channels-last grad_bev must be 16-byte aligned");
     wg.gT = const_cast<float *>(grad_bev);   // (read only by the chunk kernel)
   } else {
-    const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
-    if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
-    ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
-    SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
+    CUtensorMap g_map;
+    static const bool no_tma_load = getenv("SGV3D_NO_TMA_LOAD") != nullptr;
+    if (!no_tma_load && make_bev_map(m, const_cast<float *>(grad_bev), &g_map)) {   // (same view as the forward's map)
+      const size_t gsm = (size_t)((m.C + 7) / 8) * 2048;
+      if (int rc = set_smem(ls_grad_rows_tma_kernel, gsm)) return rc;
+      ls_grad_rows_tma_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, w.tile_ptr, w.gT, row_perm(m), g_map);
+      SGV3D_CHECK_LAUNCH("ls_grad_rows_tma_kernel");
+    } else {
+      const size_t gsm = sizeof(float) * (size_t)m.C * (kTileV + 1);
+      if (int rc = set_smem(ls_grad_rows_kernel, gsm)) return rc;
+      ls_grad_rows_kernel<<<dim3(m.ntiles, m.B), 256, gsm, s>>>(m, grad_bev, w.tile_ptr, w.gT, row_perm(m));
+      SGV3D_CHECK_LAUNCH("ls_grad_rows_kernel");
+    }
   }
   return ctx_dtype == SGV3D_DTYPE_BF16
              ? launch_backward_chunk<__nv_bfloat16>(m, wg, height, context, grad_height, grad_context, s)
