@@ -898,6 +898,46 @@ __device__ __forceinline__ void context_rows_role(const Dims &m, const CT *__res
   }
 }
 
+// The same with the TMA engine on the way in (fp32 context, LSSFPN call site): the chunk's four {32 pixels, C planes}
+// boxes of the (P, C, B*Nc) view of `context` arrive with four 3-D tensor loads (SWIZZLE_128B, one mbarrier) instead of
+// C * 128 four-byte cp.async copies; a thread then moves 16-byte chunks (4 pixels of one channel) into 4 rows.
+__device__ __forceinline__ void context_rows_tma_role(const Dims &m, float *__restrict__ ctxT, RowPerm perm,
+                                                      unsigned char *smem, int b, int chunk, const CUtensorMap *ctx_map) {
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int n = chunk / m.cpc, ci = chunk - n * m.cpc;
+  const int p0 = ci * kChunk;
+  const int npx = min(kChunk, m.P - p0);
+  // boxes on 1 KB boundaries: the swizzle uses shared-memory address bits 7-9 as the row index
+  unsigned char *box0 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  const unsigned box_bytes = (((unsigned)m.C + 7u) >> 3) * 1024u;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_arrive_expect_tx(&s_bar, (kChunk / 32) * (unsigned)m.C * 128u);   // (pixels past P: zero-filled and counted)
+    const unsigned long long mp = reinterpret_cast<unsigned long long>(ctx_map);
+    for (int k = 0; k < kChunk / 32; ++k)
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              smem_u32(box0) + k * box_bytes),
+          "l"(mp), "r"(p0 + 32 * k), "r"(0), "r"(b * m.Nc + n), "r"(smem_u32(&s_bar))
+          : "memory");
+  }
+  __syncthreads();   // the barrier is initialised before anybody waits on it
+  mbar_wait(&s_bar, 0);
+  float *dst = ctxT + ((size_t)(b * m.Nc + n) * m.P + p0) * m.Cpad;
+  for (int idx = threadIdx.x; idx < (kChunk / 4) * m.Cpad; idx += kPrepThreads) {
+    const int jq = idx / m.Cpad, e = idx - jq * m.Cpad;   // pixel quad, element of the row
+    const int c = perm.chan(e);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < m.C)
+      v = *reinterpret_cast<const float4 *>(box0 + (jq >> 3) * box_bytes + c * 128 + (((jq & 7) ^ (c & 7)) << 4));
+    float *dp = dst + (size_t)(4 * jq) * m.Cpad + e;
+    if (4 * jq + 0 < npx) dp[0] = v.x;
+    if (4 * jq + 1 < npx) dp[m.Cpad] = v.y;
+    if (4 * jq + 2 < npx) dp[2 * m.Cpad] = v.z;
+    if (4 * jq + 3 < npx) dp[3 * m.Cpad] = v.w;
+  }
+}
+
 // One launch, two kinds of CTA (blockIdx.z): run weights of a pixel chunk (ALU / latency bound) and
 // channels-last context rows of a pixel chunk (bandwidth bound) -- they overlap on every SM.
 template <typename CT, bool BSM>
@@ -905,10 +945,14 @@ __global__ void __launch_bounds__(kPrepThreads)
 ls_lift_prep_kernel(Dims m, const float *__restrict__ height, int vec16, const int *__restrict__ run_cnt,
                     const int *__restrict__ run_d, const int *__restrict__ run_dst,
                     float *__restrict__ w_pm_out, Entry *__restrict__ vm_ent_out,
-                    const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm, BsmAssembly bsm) {
+                    const CT *__restrict__ context, CT *__restrict__ ctxT, RowPerm perm, BsmAssembly bsm, int ctx_tma,
+                    const __grid_constant__ CUtensorMap ctx_map) {
   extern __shared__ __align__(128) float lift_smem[];
   if (blockIdx.z == 0)
     weights_role<BSM>(m, height, vec16, run_cnt, run_d, run_dst, w_pm_out, vm_ent_out, lift_smem, blockIdx.y, blockIdx.x, bsm);
+  else if (!BSM && sizeof(CT) == 4 && ctx_tma)   // (block-uniform)
+    context_rows_tma_role(m, reinterpret_cast<float *>(ctxT), perm, reinterpret_cast<unsigned char *>(lift_smem), blockIdx.y,
+                          blockIdx.x, &ctx_map);
   else context_rows_role<CT>(m, context, ctxT, perm, lift_smem, blockIdx.y, blockIdx.x, bsm);
 }
 
@@ -1975,30 +2019,65 @@ int launch_backward_gather(const Dims &m, const Workspace &w, int gpad, cudaStre
   return SGV3D_OK;
 }
 
+// 3-D tensor map of the fp32 context viewed as (B*Nc) cameras x C planes x P pixels (camera stride cs elements),
+// box = {32 pixels, C planes, 1 camera}, SWIZZLE_128B.
+bool make_context_map(const Dims &m, const void *context, CUtensorMap *map) {
+  typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static const Encode encode = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (getenv("SGV3D_NO_TMA_LOAD")) return (Encode) nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<Encode>(fn);
+  }();
+  if (!encode || m.P % 4 != 0 || m.cs % 4 != 0 || m.C > 256 || reinterpret_cast<uintptr_t>(context) % 16 != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)m.P, (cuuint64_t)m.C, (cuuint64_t)m.B * m.Nc};
+  const cuuint64_t strides[2] = {(cuuint64_t)m.P * sizeof(float), (cuuint64_t)m.cs * sizeof(float)};
+  const cuuint32_t box[3] = {32u, (cuuint32_t)m.C, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(context), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // weights + context rows in one launch (forward and backward need both)
 int launch_lift_prep(const Dims &m, const Workspace &w, int ctx_dtype, const float *height, const void *context,
                      bool forward, cudaStream_t s, BsmAssembly bsm = BsmAssembly{nullptr, 0, 0, 0.0f}) {
   Entry *vm_out = forward ? w.vm_ent : nullptr;
   dim3 grid(m.nchunks, m.B, 2);
   const size_t smem = sizeof(float) * (size_t)(m.D > m.C ? m.D * kChunk : m.C * (kChunk + 1));
-  const size_t smem2 = sizeof(float) * (size_t)kChunk * m.D > smem ? sizeof(float) * (size_t)kChunk * m.D : smem;
+  size_t smem2 = sizeof(float) * (size_t)kChunk * m.D > smem ? sizeof(float) * (size_t)kChunk * m.D : smem;
   const int vec16 = columns_vec16(height, m.hs, m.P) ? 1 : 0;
+  // fp32 context of the LSSFPN call site: the context role takes its tiles through TMA tensor loads (four 1 KB-aligned
+  // boxes of ceil(C / 8) KB each, plus the slack to align the first)
+  CUtensorMap ctx_map;
+  memset(&ctx_map, 0, sizeof(ctx_map));
+  int ctx_tma = 0;
+  // (small launches are latency bound and keep the cp.async role: one frame 15.5 vs 17.3 us; 64 frames 98.6 vs 92.8 us)
+  if (ctx_dtype != SGV3D_DTYPE_BF16 && !bsm.sem && m.B * m.nchunks >= 4 * kNumSMs && make_context_map(m, context, &ctx_map)) {
+    ctx_tma = 1;
+    smem2 = std::max(smem2, (size_t)(kChunk / 32) * ((m.C + 7) / 8) * 1024 + 1024);
+  }
   if (ctx_dtype == SGV3D_DTYPE_BF16) {
     if (int rc = set_smem(ls_lift_prep_kernel<__nv_bfloat16, false>, smem2)) return rc;
     ls_lift_prep_kernel<__nv_bfloat16, false><<<grid, kPrepThreads, smem2, s>>>(
         m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm, vm_out, static_cast<const __nv_bfloat16 *>(context),
-        static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m), bsm);
+        static_cast<__nv_bfloat16 *>(w.ctxT), row_perm(m), bsm, ctx_tma, ctx_map);
   } else {
     if (bsm.sem) {
       if (int rc = set_smem(ls_lift_prep_kernel<float, true>, smem2)) return rc;
       ls_lift_prep_kernel<float, true><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
                                                                   vm_out, static_cast<const float *>(context),
-                                                                  static_cast<float *>(w.ctxT), row_perm(m), bsm);
+                                                                  static_cast<float *>(w.ctxT), row_perm(m), bsm, ctx_tma, ctx_map);
     } else {
       if (int rc = set_smem(ls_lift_prep_kernel<float, false>, smem2)) return rc;
       ls_lift_prep_kernel<float, false><<<grid, kPrepThreads, smem2, s>>>(m, height, vec16, w.run_cnt, w.run_d, w.run_dst, w.w_pm,
                                                                    vm_out, static_cast<const float *>(context),
-                                                                   static_cast<float *>(w.ctxT), row_perm(m), bsm);
+                                                                   static_cast<float *>(w.ctxT), row_perm(m), bsm, ctx_tma, ctx_map);
     }
   }
   SGV3D_CHECK_LAUNCH("ls_lift_prep_kernel");
