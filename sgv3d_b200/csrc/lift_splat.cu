@@ -1639,7 +1639,8 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
   // B200 with every chunk on this path: SGV3D-BSM-R50, ~30 runs per pixel, 662 -> 590 us at 16 frames; DAIR-R50, ~12
   // runs, 382 -> 388 us): taken when at least half of the chunk's pixels have 14 runs or more (block-uniform; any
   // threshold in 12 .. 18 gives DAIR-R50 373 us, SGV3D-BSM-R50 596 us), else the run table is walked again.
-  const bool bins_in_tile = m.D <= kRowF && __syncthreads_count(cnt >= 14) >= 2 * kBwdPix;
+  // (the host sizes the tile for max(Cpad, D) rows when D <= 96: vec16_out bit 2 says the D rows fit)
+  const bool bins_in_tile = (m.D <= kRowF || (vec16_out & 4)) && __syncthreads_count(cnt >= 14) >= 2 * kBwdPix;
   float *gbin = tile;
   if (bins_in_tile) {
     float4 *z4 = reinterpret_cast<float4 *>(tile);
@@ -1767,7 +1768,7 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
     for (; dc < m.D; dc += 4) put(dc, 0.0f);
   }
   __syncthreads();
-  if (vec16_out && npx == kBwdPix) {
+  if ((vec16_out & 1) && npx == kBwdPix) {
     const int t4 = tid & 15;
     float *gh = g_height + (size_t)bn * m.ghs + p0 + 4 * t4;
     for (int d = tid >> 4; d < m.D; d += (kBwdPix * 4) >> 4)
@@ -1954,12 +1955,14 @@ template <typename CT, int NV>
 int launch_backward_chunk_cfg(const Dims &m, const Workspace &w, const float *height, const void *context,
                               float *grad_height, float *grad_context, cudaStream_t s, BsmAssembly bsm,
                               float *grad_semantic) {
-  const size_t smem = sizeof(float) * ((size_t)m.D * kBwdPix + (size_t)m.Cpad * kBwdLd);
+  // the context tile doubles as D per-bin gradient rows of 65 floats: a few more rows when D <= 96 (D = 180 would cost a resident CTA)
+  const int tile_rows = m.D <= 96 ? std::max(m.Cpad, m.D) : m.Cpad;
+  const size_t smem = sizeof(float) * ((size_t)m.D * kBwdPix + (size_t)tile_rows * kBwdLd);
   // CTAs per SM: the kernel is latency bound (dependent gather -> FMA -> shuffle chains), so a third resident CTA pays
   // for the ~14 words of spill it costs at <= 80 channels (DAIR-R50: 440 -> 385 us at 64 frames); with 96-float rows
   // the spills dominate (SGV3D-BSM-R50: 737 -> 1117 us), so those keep two.  SGV3D_BWD_OCC overrides (experiments).
   const int vec16 = columns_vec16(height, m.hs, m.P) ? 1 : 0;
-  const int vec16_out = columns_vec16(grad_height, m.ghs, m.P) ? 1 : 0;
+  const int vec16_out = (columns_vec16(grad_height, m.ghs, m.P) ? 1 : 0) | (tile_rows >= m.D ? 4 : 0);
   static const int occ_env = getenv("SGV3D_BWD_OCC") ? atoi(getenv("SGV3D_BWD_OCC")) : 0;
   const int occ = occ_env ? occ_env : (NV <= 3 ? 4 : (NV <= 5 ? 3 : 2));
 #define SGV3D_BWD_CHUNK(OCC)                                                                                   \
