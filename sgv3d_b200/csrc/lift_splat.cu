@@ -1635,12 +1635,11 @@ ls_backward_chunk_kernel(Dims m, const float *__restrict__ height, int vec16, in
   // Per-bin gradients gbin[d][pixel] live in the context tile while it is free (between the context rows moving to
   // registers and the g_ctx rows coming back): the run loop drops gw_r into the bins of run r, phase 4a reads them back
   // in one uniform pass over D -- no second walk over the run table, no round trip of gw through global memory.
-  // Needs D rows of 65 floats inside the tile's Cpad rows, and pays off when the pixels have many runs (measured on
-  // B200 with every chunk on this path: SGV3D-BSM-R50, ~30 runs per pixel, 662 -> 590 us at 16 frames; DAIR-R50, ~12
-  // runs, 382 -> 388 us): taken when at least half of the chunk's pixels have 14 runs or more (block-uniform; any
-  // threshold in 12 .. 18 gives DAIR-R50 373 us, SGV3D-BSM-R50 596 us), else the run table is walked again.
-  // (the host sizes the tile for max(Cpad, D) rows when D <= 96: vec16_out bit 2 says the D rows fit)
-  const bool bins_in_tile = (m.D <= kRowF || (vec16_out & 4)) && __syncthreads_count(cnt >= 14) >= 2 * kBwdPix;
+  // Needs D rows of 65 floats in the tile (the host sizes it for max(Cpad, D) rows when D <= 96) and pays off when the
+  // pixels have more than a few runs: taken when at least half of the chunk's pixels have 8 runs or more (block-uniform;
+  // measured on B200: thresholds 0 .. 18 are within 1 % of each other -- DAIR-R50 chunk kernel 373 -> 356 us, Rope3D-R50
+  // 346 -> 313 us, SGV3D-BSM-R50 662 -> 595 us), else the run table is walked again.
+  const bool bins_in_tile = (m.D <= kRowF || (vec16_out & 4)) && __syncthreads_count(cnt >= 8) >= 2 * kBwdPix;
   float *gbin = tile;
   if (bins_in_tile) {
     float4 *z4 = reinterpret_cast<float4 *>(tile);
